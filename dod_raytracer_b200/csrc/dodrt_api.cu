@@ -1,0 +1,602 @@
+// dodrt_api.cu -- the extern "C" boundary declared in include/dodrt.h.
+//
+// Host-side responsibilities only: argument validation, scene upload (one replica per GPU, kept
+// resident in HBM for the lifetime of the handle), staging of host buffers, kernel launches and
+// error translation.  All ray/shape arithmetic lives in dodrt_device.cuh / dodrt_kernels.cu.
+// There is deliberately no CPU implementation behind any entry point.
+#include "dodrt_kernels.cuh"
+
+#include <atomic>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+#include <new>
+#include <string>
+#include <vector>
+
+using namespace dodrt;
+
+namespace {
+
+thread_local std::string g_lastError;
+
+int fail(int code, const char *fmt, ...)
+{
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof(buf), fmt, ap);
+    va_end(ap);
+    g_lastError = buf;
+    return code;
+}
+
+#define CUDA_TRY(expr)                                                                                       \
+    do {                                                                                                     \
+        cudaError_t e__ = (expr);                                                                            \
+        if (e__ != cudaSuccess) {                                                                            \
+            return fail(DODRT_E_CUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(e__), __FILE__,     \
+                        __LINE__);                                                                           \
+        }                                                                                                    \
+    } while (0)
+
+constexpr int kCounterSlots = 256;
+
+struct DeviceGuard {
+    int prev = -1;
+    bool ok = false;
+    explicit DeviceGuard(int device)
+    {
+        if (cudaGetDevice(&prev) == cudaSuccess && cudaSetDevice(device) == cudaSuccess) {
+            ok = true;
+        }
+    }
+    ~DeviceGuard()
+    {
+        if (prev >= 0) {
+            cudaSetDevice(prev);
+        }
+    }
+};
+
+template <typename T> void freeDevice(T *&p)
+{
+    if (p) {
+        cudaFree(const_cast<void *>(static_cast<const void *>(p)));
+        p = nullptr;
+    }
+}
+
+} // namespace
+
+struct dodrt_scene {
+    int device = 0;
+    DeviceScene dev{};
+    uint2 *d_nodes = nullptr;
+    float4 *d_tris = nullptr;
+    float *d_spheres = nullptr;
+    float *d_planes = nullptr;
+    dodrt_cylinder *d_cylinders = nullptr;
+    float *d_boxes = nullptr;
+    unsigned long long *d_counters = nullptr;
+    std::atomic<uint32_t> nextCounter{0};
+    std::atomic<uint64_t> launches{0};
+    LaunchConfig cfg[3]{};
+    uint32_t treeDepth = 0;
+    std::mutex mutex; // guards scene mutation and the lazily created staging stream
+    cudaStream_t stream = nullptr;
+};
+
+namespace {
+
+// depth of the DFS pre-order tree (left child = node+1, right child index in word0 >> 2), and
+// validation of every index the kernels will dereference
+int validateTree(const uint64_t *nodes, uint32_t numNodes, uint32_t numLanes, uint32_t *depthOut)
+{
+    if (numNodes == 0) {
+        *depthOut = 0;
+        return DODRT_OK;
+    }
+    struct Item {
+        uint32_t node, depth;
+    };
+    std::vector<Item> stack;
+    stack.push_back({0, 1});
+    uint32_t maxDepth = 0;
+    uint64_t visited = 0;
+    while (!stack.empty()) {
+        Item it = stack.back();
+        stack.pop_back();
+        if (it.node >= numNodes) {
+            return fail(DODRT_E_INVALID, "kd-tree child index %u out of range (%u nodes)", it.node, numNodes);
+        }
+        if (++visited > numNodes) {
+            return fail(DODRT_E_INVALID, "kd-tree is not a tree (cycle or shared node)");
+        }
+        maxDepth = it.depth > maxDepth ? it.depth : maxDepth;
+        const uint32_t w0 = (uint32_t)(nodes[it.node] & 0xFFFFFFFFu);
+        const uint32_t w1 = (uint32_t)(nodes[it.node] >> 32);
+        if ((w0 & 3u) == kLeafFlag) {
+            const uint64_t n = w0 >> 2;
+            if (n && (uint64_t)w1 + n > numLanes) {
+                return fail(DODRT_E_INVALID, "leaf %u references lanes [%u,%llu) beyond %u", it.node, w1,
+                            (unsigned long long)(w1 + n), numLanes);
+            }
+        } else {
+            stack.push_back({w0 >> 2, it.depth + 1});
+            stack.push_back({it.node + 1, it.depth + 1});
+        }
+    }
+    *depthOut = maxDepth;
+    return DODRT_OK;
+}
+
+int checkFrame(const dodrt_frame *f)
+{
+    if (!f) return fail(DODRT_E_INVALID, "frame is NULL");
+    if (f->width == 0 || f->height == 0) return fail(DODRT_E_INVALID, "empty frame %ux%u", f->width, f->height);
+    if (f->tile_w == 0 || f->tile_h == 0 || (f->tile_w % 8) || (f->tile_h % 4)) {
+        return fail(DODRT_E_INVALID, "tile %ux%u must be a non-zero multiple of 8x4", f->tile_w, f->tile_h);
+    }
+    if (f->tile_stride == 0) return fail(DODRT_E_INVALID, "tile_stride must be >= 1");
+    if ((uint64_t)f->width * f->height >= 0xFFFFFFFFull) return fail(DODRT_E_INVALID, "frame too large");
+    return DODRT_OK;
+}
+
+void frameTiles(const dodrt_frame *f, uint32_t *tilesX, uint32_t *localTiles)
+{
+    const uint32_t tx = (f->width + f->tile_w - 1) / f->tile_w;
+    const uint32_t ty = (f->height + f->tile_h - 1) / f->tile_h;
+    const uint64_t total = (uint64_t)tx * ty;
+    *tilesX = tx;
+    *localTiles = f->first_tile < total ? (uint32_t)((total - f->first_tile + f->tile_stride - 1) / f->tile_stride) : 0;
+}
+
+uint64_t frameSlots(const dodrt_frame *f)
+{
+    uint32_t tx, lt;
+    frameTiles(f, &tx, &lt);
+    return (uint64_t)lt * f->tile_w * f->tile_h;
+}
+
+unsigned long long *nextCounter(dodrt_scene *s)
+{
+    return s->d_counters + (s->nextCounter.fetch_add(1) % kCounterSlots);
+}
+
+int ensureStream(dodrt_scene *s)
+{
+    std::lock_guard<std::mutex> lock(s->mutex);
+    if (!s->stream) {
+        CUDA_TRY(cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking));
+    }
+    return DODRT_OK;
+}
+
+int launchFrame(dodrt_scene *s, TraceMode mode, const dodrt_frame *frame, const float *d_xs, const float *d_ys,
+                dodrt_hit *d_hits, const float *light, uint8_t *d_visible, cudaStream_t stream)
+{
+    TraceParams p{};
+    p.scene = s->dev;
+    p.classes = frame->classes;
+    p.frame = *frame;
+    uint32_t localTiles;
+    frameTiles(frame, &p.tiles_x, &localTiles);
+    p.count = (uint64_t)localTiles * frame->tile_w * frame->tile_h;
+    p.hits = d_hits;
+    p.xs = d_xs;
+    p.ys = d_ys;
+    p.visible = d_visible;
+    if (light) {
+        p.light[0] = light[0];
+        p.light[1] = light[1];
+        p.light[2] = light[2];
+    }
+    p.counter = nextCounter(s);
+    if (p.count == 0) {
+        return DODRT_OK;
+    }
+    CUDA_TRY(launch_trace(mode, p, s->cfg[mode], stream));
+    s->launches.fetch_add(1);
+    return DODRT_OK;
+}
+
+} // namespace
+
+extern "C" {
+
+int dodrt_abi_version(void) { return DODRT_ABI_VERSION; }
+
+const char *dodrt_last_error(void) { return g_lastError.c_str(); }
+
+int dodrt_device_count(int *count)
+{
+    if (!count) return fail(DODRT_E_INVALID, "count is NULL");
+    *count = 0;
+    CUDA_TRY(cudaGetDeviceCount(count));
+    return DODRT_OK;
+}
+
+int dodrt_scene_create(int device, dodrt_scene **scene)
+{
+    if (!scene) return fail(DODRT_E_INVALID, "scene is NULL");
+    *scene = nullptr;
+    int count = 0;
+    CUDA_TRY(cudaGetDeviceCount(&count));
+    if (device < 0 || device >= count) return fail(DODRT_E_INVALID, "device %d out of range (%d devices)", device, count);
+    DeviceGuard guard(device);
+    if (!guard.ok) return fail(DODRT_E_CUDA, "cannot select device %d", device);
+    dodrt_scene *s = new (std::nothrow) dodrt_scene();
+    if (!s) return fail(DODRT_E_NOMEM, "out of host memory");
+    s->device = device;
+    s->dev.epsilon = 0.0001f; // Config::Epsilon default, config.h:9
+    cudaError_t e = cudaMalloc(&s->d_counters, sizeof(unsigned long long) * kCounterSlots);
+    for (int m = 0; m < 3 && e == cudaSuccess; m++) {
+        e = trace_launch_config(device, (TraceMode)m, &s->cfg[m]);
+    }
+    if (e != cudaSuccess) {
+        cudaFree(s->d_counters);
+        delete s;
+        return fail(DODRT_E_CUDA, "scene_create: %s", cudaGetErrorString(e));
+    }
+    *scene = s;
+    return DODRT_OK;
+}
+
+int dodrt_scene_destroy(dodrt_scene *s)
+{
+    if (!s) return DODRT_OK;
+    DeviceGuard guard(s->device);
+    cudaDeviceSynchronize();
+    if (s->stream) cudaStreamDestroy(s->stream);
+    freeDevice(s->d_nodes);
+    freeDevice(s->d_tris);
+    freeDevice(s->d_spheres);
+    freeDevice(s->d_planes);
+    freeDevice(s->d_cylinders);
+    freeDevice(s->d_boxes);
+    freeDevice(s->d_counters);
+    delete s;
+    return DODRT_OK;
+}
+
+int dodrt_scene_set_kdtree(dodrt_scene *s, const uint64_t *nodes, uint32_t num_nodes, const float *tri_lanes,
+                           uint32_t num_tri_lanes, const float bounds[6])
+{
+    if (!s) return fail(DODRT_E_INVALID, "scene is NULL");
+    if ((num_nodes && !nodes) || (num_tri_lanes && !tri_lanes) || !bounds) {
+        return fail(DODRT_E_INVALID, "NULL array with non-zero count");
+    }
+    if ((uint64_t)num_tri_lanes * kLane >= (1ull << DODRT_KIND_SHIFT)) {
+        return fail(DODRT_E_LIMIT, "%u lanes exceed the %u-bit triangle id space", num_tri_lanes, DODRT_KIND_SHIFT);
+    }
+    uint32_t depth = 0;
+    int rc = validateTree(nodes, num_nodes, num_tri_lanes, &depth);
+    if (rc != DODRT_OK) return rc;
+    if (depth > (uint32_t)kMaxStack) {
+        return fail(DODRT_E_LIMIT, "kd-tree depth %u exceeds the traversal stack (%d)", depth, kMaxStack);
+    }
+    std::lock_guard<std::mutex> lock(s->mutex);
+    DeviceGuard guard(s->device);
+    if (!guard.ok) return fail(DODRT_E_CUDA, "cannot select device %d", s->device);
+    freeDevice(s->d_nodes);
+    freeDevice(s->d_tris);
+    s->dev.nodes = nullptr;
+    s->dev.tris = nullptr;
+    s->dev.num_nodes = 0;
+    s->dev.num_tri_lanes = 0;
+    if (num_nodes) {
+        CUDA_TRY(cudaMalloc(&s->d_nodes, (size_t)num_nodes * sizeof(uint2)));
+        CUDA_TRY(cudaMemcpy(s->d_nodes, nodes, (size_t)num_nodes * sizeof(uint2), cudaMemcpyHostToDevice));
+    }
+    if (num_tri_lanes) {
+        float *d_lanes = nullptr;
+        const size_t laneBytes = (size_t)num_tri_lanes * 288;
+        CUDA_TRY(cudaMalloc(&d_lanes, laneBytes));
+        cudaError_t e = cudaMemcpy(d_lanes, tri_lanes, laneBytes, cudaMemcpyHostToDevice);
+        if (e == cudaSuccess) e = cudaMalloc(&s->d_tris, (size_t)num_tri_lanes * kLane * 3 * sizeof(float4));
+        if (e == cudaSuccess) e = launch_repack_triangles(d_lanes, num_tri_lanes, s->d_tris, nullptr);
+        if (e == cudaSuccess) e = cudaDeviceSynchronize();
+        cudaFree(d_lanes);
+        if (e != cudaSuccess) return fail(DODRT_E_CUDA, "triangle upload: %s", cudaGetErrorString(e));
+        s->launches.fetch_add(1);
+    }
+    s->dev.nodes = s->d_nodes;
+    s->dev.tris = s->d_tris;
+    s->dev.num_nodes = num_nodes;
+    s->dev.num_tri_lanes = num_tri_lanes;
+    for (int i = 0; i < 3; i++) {
+        s->dev.bmin[i] = bounds[i];
+        s->dev.bmax[i] = bounds[3 + i];
+    }
+    s->treeDepth = depth;
+    return DODRT_OK;
+}
+
+static int uploadLanes(dodrt_scene *s, float **slot, const float **view, uint32_t *countField, const float *lanes,
+                       uint32_t count, uint32_t floatsPerLane)
+{
+    if (!s) return fail(DODRT_E_INVALID, "scene is NULL");
+    if (count && !lanes) return fail(DODRT_E_INVALID, "NULL lanes with non-zero count");
+    std::lock_guard<std::mutex> lock(s->mutex);
+    DeviceGuard guard(s->device);
+    if (!guard.ok) return fail(DODRT_E_CUDA, "cannot select device %d", s->device);
+    freeDevice(*slot);
+    *view = nullptr;
+    *countField = 0;
+    if (count) {
+        const size_t bytes = (size_t)((count + kLane - 1) / kLane) * floatsPerLane * sizeof(float);
+        CUDA_TRY(cudaMalloc(slot, bytes));
+        CUDA_TRY(cudaMemcpy(*slot, lanes, bytes, cudaMemcpyHostToDevice));
+    }
+    *view = *slot;
+    *countField = count;
+    return DODRT_OK;
+}
+
+int dodrt_scene_set_spheres(dodrt_scene *s, const float *sphere_lanes, uint32_t num_spheres)
+{
+    if (!s) return fail(DODRT_E_INVALID, "scene is NULL");
+    return uploadLanes(s, &s->d_spheres, &s->dev.sphere_lanes, &s->dev.num_spheres, sphere_lanes, num_spheres, 4 * kLane);
+}
+
+int dodrt_scene_set_planes(dodrt_scene *s, const float *plane_lanes, uint32_t num_planes)
+{
+    if (!s) return fail(DODRT_E_INVALID, "scene is NULL");
+    return uploadLanes(s, &s->d_planes, &s->dev.plane_lanes, &s->dev.num_planes, plane_lanes, num_planes, 6 * kLane);
+}
+
+int dodrt_scene_set_boxes(dodrt_scene *s, const float *box_lanes, uint32_t num_boxes)
+{
+    if (!s) return fail(DODRT_E_INVALID, "scene is NULL");
+    return uploadLanes(s, &s->d_boxes, &s->dev.box_lanes, &s->dev.num_boxes, box_lanes, num_boxes, 6 * kLane);
+}
+
+int dodrt_scene_set_cylinders(dodrt_scene *s, const dodrt_cylinder *cylinders, uint32_t num_cylinders)
+{
+    if (!s) return fail(DODRT_E_INVALID, "scene is NULL");
+    if (num_cylinders && !cylinders) return fail(DODRT_E_INVALID, "NULL cylinders with non-zero count");
+    std::lock_guard<std::mutex> lock(s->mutex);
+    DeviceGuard guard(s->device);
+    if (!guard.ok) return fail(DODRT_E_CUDA, "cannot select device %d", s->device);
+    freeDevice(s->d_cylinders);
+    s->dev.cylinders = nullptr;
+    s->dev.num_cylinders = 0;
+    if (num_cylinders) {
+        CUDA_TRY(cudaMalloc(&s->d_cylinders, sizeof(dodrt_cylinder) * num_cylinders));
+        CUDA_TRY(cudaMemcpy(s->d_cylinders, cylinders, sizeof(dodrt_cylinder) * num_cylinders, cudaMemcpyHostToDevice));
+    }
+    s->dev.cylinders = s->d_cylinders;
+    s->dev.num_cylinders = num_cylinders;
+    return DODRT_OK;
+}
+
+int dodrt_scene_set_epsilon(dodrt_scene *s, float epsilon)
+{
+    if (!s) return fail(DODRT_E_INVALID, "scene is NULL");
+    std::lock_guard<std::mutex> lock(s->mutex);
+    s->dev.epsilon = epsilon;
+    return DODRT_OK;
+}
+
+// ---- device-resident entry points ---------------------------------------------------------------
+
+int dodrt_intersect_device(dodrt_scene *s, const dodrt_ray *d_rays, uint64_t num_rays, uint32_t classes,
+                           dodrt_hit *d_hits, void *stream)
+{
+    if (!s) return fail(DODRT_E_INVALID, "scene is NULL");
+    if (num_rays == 0) return DODRT_OK;
+    if (!d_rays || !d_hits) return fail(DODRT_E_INVALID, "NULL ray/hit buffer");
+    DeviceGuard guard(s->device);
+    if (!guard.ok) return fail(DODRT_E_CUDA, "cannot select device %d", s->device);
+    TraceParams p{};
+    p.scene = s->dev;
+    p.classes = classes;
+    p.rays = d_rays;
+    p.count = num_rays;
+    p.hits = d_hits;
+    p.counter = nextCounter(s);
+    CUDA_TRY(launch_trace(kModeRays, p, s->cfg[kModeRays], static_cast<cudaStream_t>(stream)));
+    s->launches.fetch_add(1);
+    return DODRT_OK;
+}
+
+int dodrt_trace_primary_device(dodrt_scene *s, const dodrt_frame *frame, const float *d_xs, const float *d_ys,
+                               dodrt_hit *d_hits, void *stream)
+{
+    if (!s) return fail(DODRT_E_INVALID, "scene is NULL");
+    int rc = checkFrame(frame);
+    if (rc != DODRT_OK) return rc;
+    if (!d_xs || !d_ys || !d_hits) return fail(DODRT_E_INVALID, "NULL table/hit buffer");
+    DeviceGuard guard(s->device);
+    if (!guard.ok) return fail(DODRT_E_CUDA, "cannot select device %d", s->device);
+    return launchFrame(s, kModePrimary, frame, d_xs, d_ys, d_hits, nullptr, nullptr, static_cast<cudaStream_t>(stream));
+}
+
+int dodrt_trace_shadow_device(dodrt_scene *s, const dodrt_frame *frame, const float *d_xs, const float *d_ys,
+                              const dodrt_hit *d_hits, const float light[3], uint8_t *d_visible, void *stream)
+{
+    if (!s) return fail(DODRT_E_INVALID, "scene is NULL");
+    int rc = checkFrame(frame);
+    if (rc != DODRT_OK) return rc;
+    if (!d_xs || !d_ys || !d_hits || !light || !d_visible) return fail(DODRT_E_INVALID, "NULL argument");
+    DeviceGuard guard(s->device);
+    if (!guard.ok) return fail(DODRT_E_CUDA, "cannot select device %d", s->device);
+    return launchFrame(s, kModeShadow, frame, d_xs, d_ys, const_cast<dodrt_hit *>(d_hits), light, d_visible,
+                       static_cast<cudaStream_t>(stream));
+}
+
+// ---- host-buffer entry points -------------------------------------------------------------------
+
+int dodrt_intersect(dodrt_scene *s, const dodrt_ray *rays, uint64_t num_rays, uint32_t classes, dodrt_hit *hits)
+{
+    if (!s) return fail(DODRT_E_INVALID, "scene is NULL");
+    if (num_rays == 0) return DODRT_OK;
+    if (!rays || !hits) return fail(DODRT_E_INVALID, "NULL ray/hit buffer");
+    int rc = ensureStream(s);
+    if (rc != DODRT_OK) return rc;
+    DeviceGuard guard(s->device);
+    if (!guard.ok) return fail(DODRT_E_CUDA, "cannot select device %d", s->device);
+    dodrt_ray *d_rays = nullptr;
+    dodrt_hit *d_hits = nullptr;
+    cudaStream_t st = s->stream;
+    CUDA_TRY(cudaMallocAsync(&d_rays, num_rays * sizeof(dodrt_ray), st));
+    cudaError_t e = cudaMallocAsync(&d_hits, num_rays * sizeof(dodrt_hit), st);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(d_rays, rays, num_rays * sizeof(dodrt_ray), cudaMemcpyHostToDevice, st);
+    if (e == cudaSuccess) {
+        rc = dodrt_intersect_device(s, d_rays, num_rays, classes, d_hits, st);
+        if (rc == DODRT_OK) {
+            e = cudaMemcpyAsync(hits, d_hits, num_rays * sizeof(dodrt_hit), cudaMemcpyDeviceToHost, st);
+        }
+    }
+    if (d_rays) cudaFreeAsync(d_rays, st);
+    if (d_hits) cudaFreeAsync(d_hits, st);
+    cudaError_t es = cudaStreamSynchronize(st);
+    if (rc != DODRT_OK) return rc;
+    if (e == cudaSuccess) e = es;
+    if (e != cudaSuccess) return fail(DODRT_E_CUDA, "dodrt_intersect: %s", cudaGetErrorString(e));
+    return DODRT_OK;
+}
+
+int dodrt_trace_frame(dodrt_scene *s, const dodrt_frame *frame, const float *xs, const float *ys, const float *lights,
+                      uint32_t num_lights, dodrt_hit *hits, uint8_t *visible)
+{
+    if (!s) return fail(DODRT_E_INVALID, "scene is NULL");
+    int rc = checkFrame(frame);
+    if (rc != DODRT_OK) return rc;
+    if (!xs || !ys || !hits) return fail(DODRT_E_INVALID, "NULL table/hit buffer");
+    if (num_lights && (!lights || !visible)) return fail(DODRT_E_INVALID, "NULL lights/visible buffer");
+    rc = ensureStream(s);
+    if (rc != DODRT_OK) return rc;
+    DeviceGuard guard(s->device);
+    if (!guard.ok) return fail(DODRT_E_CUDA, "cannot select device %d", s->device);
+    cudaStream_t st = s->stream;
+    const uint64_t slots = frame->compact ? frameSlots(frame) : (uint64_t)frame->width * frame->height;
+    if (slots == 0) return DODRT_OK;
+    float *d_tables = nullptr;
+    dodrt_hit *d_hits = nullptr;
+    uint8_t *d_vis = nullptr;
+    const size_t tableFloats = (size_t)frame->width + frame->height;
+    CUDA_TRY(cudaMallocAsync(&d_tables, tableFloats * sizeof(float), st));
+    cudaError_t e = cudaMallocAsync(&d_hits, slots * sizeof(dodrt_hit), st);
+    if (e == cudaSuccess && num_lights) e = cudaMallocAsync(&d_vis, slots * (size_t)num_lights, st);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(d_tables, xs, frame->width * sizeof(float), cudaMemcpyHostToDevice, st);
+    if (e == cudaSuccess) {
+        e = cudaMemcpyAsync(d_tables + frame->width, ys, frame->height * sizeof(float), cudaMemcpyHostToDevice, st);
+    }
+    if (e == cudaSuccess && !frame->compact) {
+        // pixels of tiles that belong to other ranks must read as "miss" / "not visible"
+        e = cudaMemsetAsync(d_hits, 0xFF, slots * sizeof(dodrt_hit), st);
+        if (e == cudaSuccess && num_lights) e = cudaMemsetAsync(d_vis, 0, slots * (size_t)num_lights, st);
+    }
+    if (e == cudaSuccess) {
+        rc = launchFrame(s, kModePrimary, frame, d_tables, d_tables + frame->width, d_hits, nullptr, nullptr, st);
+        for (uint32_t l = 0; l < num_lights && rc == DODRT_OK; l++) {
+            rc = launchFrame(s, kModeShadow, frame, d_tables, d_tables + frame->width, d_hits, lights + 3 * l,
+                             d_vis + slots * l, st);
+        }
+        if (rc == DODRT_OK) {
+            e = cudaMemcpyAsync(hits, d_hits, slots * sizeof(dodrt_hit), cudaMemcpyDeviceToHost, st);
+            if (e == cudaSuccess && num_lights) {
+                e = cudaMemcpyAsync(visible, d_vis, slots * (size_t)num_lights, cudaMemcpyDeviceToHost, st);
+            }
+        }
+    }
+    if (d_tables) cudaFreeAsync(d_tables, st);
+    if (d_hits) cudaFreeAsync(d_hits, st);
+    if (d_vis) cudaFreeAsync(d_vis, st);
+    cudaError_t es = cudaStreamSynchronize(st);
+    if (rc != DODRT_OK) return rc;
+    if (e == cudaSuccess) e = es;
+    if (e != cudaSuccess) return fail(DODRT_E_CUDA, "dodrt_trace_frame: %s", cudaGetErrorString(e));
+    return DODRT_OK;
+}
+
+int dodrt_trace_primary(dodrt_scene *s, const dodrt_frame *frame, const float *xs, const float *ys, dodrt_hit *hits)
+{
+    return dodrt_trace_frame(s, frame, xs, ys, nullptr, 0, hits, nullptr);
+}
+
+int dodrt_trace_shadow(dodrt_scene *s, const dodrt_frame *frame, const float *xs, const float *ys,
+                       const dodrt_hit *hits, const float light[3], uint8_t *visible)
+{
+    if (!s) return fail(DODRT_E_INVALID, "scene is NULL");
+    int rc = checkFrame(frame);
+    if (rc != DODRT_OK) return rc;
+    if (!xs || !ys || !hits || !light || !visible) return fail(DODRT_E_INVALID, "NULL argument");
+    rc = ensureStream(s);
+    if (rc != DODRT_OK) return rc;
+    DeviceGuard guard(s->device);
+    if (!guard.ok) return fail(DODRT_E_CUDA, "cannot select device %d", s->device);
+    cudaStream_t st = s->stream;
+    const uint64_t slots = frame->compact ? frameSlots(frame) : (uint64_t)frame->width * frame->height;
+    if (slots == 0) return DODRT_OK;
+    float *d_tables = nullptr;
+    dodrt_hit *d_hits = nullptr;
+    uint8_t *d_vis = nullptr;
+    CUDA_TRY(cudaMallocAsync(&d_tables, ((size_t)frame->width + frame->height) * sizeof(float), st));
+    cudaError_t e = cudaMallocAsync(&d_hits, slots * sizeof(dodrt_hit), st);
+    if (e == cudaSuccess) e = cudaMallocAsync(&d_vis, slots, st);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(d_tables, xs, frame->width * sizeof(float), cudaMemcpyHostToDevice, st);
+    if (e == cudaSuccess) {
+        e = cudaMemcpyAsync(d_tables + frame->width, ys, frame->height * sizeof(float), cudaMemcpyHostToDevice, st);
+    }
+    if (e == cudaSuccess) e = cudaMemcpyAsync(d_hits, hits, slots * sizeof(dodrt_hit), cudaMemcpyHostToDevice, st);
+    if (e == cudaSuccess) e = cudaMemsetAsync(d_vis, 0, slots, st);
+    if (e == cudaSuccess) {
+        rc = launchFrame(s, kModeShadow, frame, d_tables, d_tables + frame->width, d_hits, light, d_vis, st);
+        if (rc == DODRT_OK) e = cudaMemcpyAsync(visible, d_vis, slots, cudaMemcpyDeviceToHost, st);
+    }
+    if (d_tables) cudaFreeAsync(d_tables, st);
+    if (d_hits) cudaFreeAsync(d_hits, st);
+    if (d_vis) cudaFreeAsync(d_vis, st);
+    cudaError_t es = cudaStreamSynchronize(st);
+    if (rc != DODRT_OK) return rc;
+    if (e == cudaSuccess) e = es;
+    if (e != cudaSuccess) return fail(DODRT_E_CUDA, "dodrt_trace_shadow: %s", cudaGetErrorString(e));
+    return DODRT_OK;
+}
+
+// ---- frame helpers ------------------------------------------------------------------------------
+
+int dodrt_frame_local_pixels(const dodrt_frame *frame, uint64_t *slots)
+{
+    int rc = checkFrame(frame);
+    if (rc != DODRT_OK) return rc;
+    if (!slots) return fail(DODRT_E_INVALID, "slots is NULL");
+    *slots = frameSlots(frame);
+    return DODRT_OK;
+}
+
+int dodrt_frame_pixel_map(const dodrt_frame *f, uint32_t *pixel_of_slot, uint64_t slots)
+{
+    int rc = checkFrame(f);
+    if (rc != DODRT_OK) return rc;
+    if (!pixel_of_slot && slots) return fail(DODRT_E_INVALID, "pixel_of_slot is NULL");
+    if (slots != frameSlots(f)) return fail(DODRT_E_INVALID, "slots does not match the frame description");
+    uint32_t tilesX, localTiles;
+    frameTiles(f, &tilesX, &localTiles);
+    const uint32_t tilePixels = f->tile_w * f->tile_h;
+    const uint32_t bpr = f->tile_w >> 3;
+    for (uint64_t slot = 0; slot < slots; slot++) { // same mapping as slot_to_pixel in dodrt_kernels.cu
+        const uint32_t localTile = (uint32_t)(slot / tilePixels), in = (uint32_t)(slot % tilePixels);
+        const uint32_t tile = f->first_tile + localTile * f->tile_stride;
+        const uint32_t tx = tile % tilesX, ty = tile / tilesX;
+        const uint32_t block = in >> 5, lane = in & 31u;
+        const uint32_t col = tx * f->tile_w + (block % bpr) * 8 + (lane & 7u);
+        const uint32_t row = ty * f->tile_h + (block / bpr) * 4 + (lane >> 3);
+        pixel_of_slot[slot] = (col < f->width && row < f->height) ? row * f->width + col : 0xFFFFFFFFu;
+    }
+    return DODRT_OK;
+}
+
+int dodrt_scene_launch_count(dodrt_scene *s, uint64_t *launches)
+{
+    if (!s || !launches) return fail(DODRT_E_INVALID, "NULL argument");
+    *launches = s->launches.load();
+    return DODRT_OK;
+}
+
+} // extern "C"

@@ -1,0 +1,411 @@
+// dodrt_device.cuh -- device-side scene view and intersection routines (sm_100a).
+//
+// Arithmetic contract: fp32, round-to-nearest, NO fused multiply-add (this
+// translation unit is compiled with -fmad=false, so every a*b+c below is mul.rn then add.rn), IEEE
+// div.rn / sqrt.rn (nvcc defaults -prec-div=true -prec-sqrt=true), denormals kept (-ftz=false), and
+// every expression keeps the reference's association order.  Comparisons are written exactly as the
+// reference writes them so that NaN/inf (axis-parallel rays: 0*inf in the slab test) take the same
+// branches; never replace them with fminf/fmaxf.
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+
+#include "../../include/dodrt.h"
+
+namespace dodrt {
+
+constexpr int kLane = 8;        // c_triangleLaneSz triangle.h:32, c_sphereLaneSz sphere.cpp:11
+constexpr int kMaxStack = 32;   // >= KDTree::m_maxDepth (kdtree.cpp:72); checked at upload
+constexpr uint32_t kLeafFlag = 3u;
+
+// One triangle as the traversal kernels read it: 48 bytes = 3 x LDG.128.
+//   q0 = (A.x, A.y, A.z, AB.x)  q1 = (AB.y, AB.z, AC.x, AC.y)  q2 = (AC.z, 0, 0, 0)
+// AB = B - A and AC = C - A are the reference's first two operations per triangle
+// (triangle.cpp:66-67); doing the same sub.rn once at upload is bit-identical.
+// Index of a triangle in this array == its reference id (laneIdx*8 + slot, triangle.cpp:136).
+struct DeviceScene {
+    const uint2 *nodes;     // kdtree.h:16-48, 8 B each
+    const float4 *tris;     // 3 x float4 per triangle slot
+    uint32_t num_nodes;
+    uint32_t num_tri_lanes;
+    float bmin[3], bmax[3]; // KDTree::m_bounds
+    const float *sphere_lanes; // x[8] y[8] z[8] r2[8]
+    uint32_t num_spheres;
+    const float *plane_lanes;  // px py pz nx ny nz [8]
+    uint32_t num_planes;
+    const dodrt_cylinder *cylinders;
+    uint32_t num_cylinders;
+    const float *box_lanes;    // minx miny minz maxx maxy maxz [8]
+    uint32_t num_boxes;
+    float epsilon;
+};
+
+struct Hit {
+    float t;
+    uint32_t prim;
+    float u, v;
+};
+
+// avxDot avx_utils.h:13-22 == glm::dot: (x1*x2 + y1*y2) + z1*z2
+__device__ __forceinline__ float dot3(float ax, float ay, float az, float bx, float by, float bz)
+{
+    float px = ax * bx;
+    float py = ay * by;
+    float pz = az * bz;
+    float acc = px + py;
+    return acc + pz;
+}
+
+// AxisAlignedBoundingBox::intersect, box.cpp:33-53
+__device__ __forceinline__ bool slab(const float bmin[3], const float bmax[3], const float o[3], const float inv[3],
+                                     float clip, float &tminOut, float &tmaxOut)
+{
+    float tmin = 0.0f;
+    float tmax = clip;
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+        float tNear = (bmin[i] - o[i]) * inv[i];
+        float tFar = (bmax[i] - o[i]) * inv[i];
+        if (tNear > tFar) {
+            float tmp = tNear;
+            tNear = tFar;
+            tFar = tmp;
+        }
+        tmin = tNear > tmin ? tNear : tmin;
+        tmax = tFar < tmax ? tFar : tmax;
+        if (tmin > tmax) {
+            return false;
+        }
+    }
+    tminOut = tmin;
+    tmaxOut = tmax;
+    return true;
+}
+
+// One triangle of Triangle::intersectInRange (triangle.cpp:66-139).  `maxDist` is the running
+// maximumDistance: the reference's lane-start compare (triangle.cpp:109-111) and running compare
+// (triangle.cpp:133) collapse to this one strict `<` because the running value never grows.
+__device__ __forceinline__ bool triangle_test(const float4 q0, const float4 q1, const float4 q2, const float o[3],
+                                              const float d[3], float maxDist, float &tOut, float &uOut, float &vOut)
+{
+    const float Ax = q0.x, Ay = q0.y, Az = q0.z;
+    const float ABx = q0.w, ABy = q1.x, ABz = q1.y;
+    const float ACx = q1.z, ACy = q1.w, ACz = q2.x;
+    float px = d[1] * ACz - d[2] * ACy; // avxCross(rayDir, AC)
+    float py = d[2] * ACx - d[0] * ACz;
+    float pz = d[0] * ACy - d[1] * ACx;
+    float det = dot3(px, py, pz, ABx, ABy, ABz);
+    if (!(fabsf(det) > 0.0f)) {
+        return false;
+    }
+    float inv_det = 1.0f / det;
+    float tx = o[0] - Ax, ty = o[1] - Ay, tz = o[2] - Az;
+    float u = dot3(tx, ty, tz, px, py, pz) * inv_det;
+    if (!(u > 0.0f && u < 1.0f)) {
+        return false;
+    }
+    float qx = ty * ABz - tz * ABy; // avxCross(tvec, AB)
+    float qy = tz * ABx - tx * ABz;
+    float qz = tx * ABy - ty * ABx;
+    float v = dot3(d[0], d[1], d[2], qx, qy, qz) * inv_det;
+    if (!(v > 0.0f && (u + v) < 1.0f)) {
+        return false;
+    }
+    float t = dot3(ACx, ACy, ACz, qx, qy, qz) * inv_det;
+    if (!(t > 0.0f && t < maxDist)) {
+        return false;
+    }
+    tOut = t;
+    uOut = u;
+    vOut = v;
+    return true;
+}
+
+// Sphere::intersect_impl, sphere.cpp:26-160 (lane-structured for the any-hit break, sphere.cpp:138-141)
+__device__ __forceinline__ bool sphere_query(const DeviceScene &s, const float o[3], const float d[3], bool any,
+                                             float clip, Hit &hit)
+{
+    float recordT = clip;
+    uint32_t closest = DODRT_MISS;
+    const uint32_t numLanes = (s.num_spheres + kLane - 1) / kLane;
+    for (uint32_t i = 0; i < numLanes; i++) {
+        const float4 *lane = reinterpret_cast<const float4 *>(s.sphere_lanes + (size_t)i * 4 * kLane);
+        uint32_t minIdx = 0;
+        float minDist = recordT;
+#pragma unroll
+        for (int h = 0; h < 2; h++) {
+            const float4 X = __ldg(lane + 0 + h), Y = __ldg(lane + 2 + h), Z = __ldg(lane + 4 + h), R = __ldg(lane + 6 + h);
+            const float xs[4] = {X.x, X.y, X.z, X.w}, ys[4] = {Y.x, Y.y, Y.z, Y.w};
+            const float zs[4] = {Z.x, Z.y, Z.z, Z.w}, rs[4] = {R.x, R.y, R.z, R.w};
+#pragma unroll
+            for (int k = 0; k < 4; k++) {
+                const uint32_t j = h * 4 + k;
+                if (i * kLane + j >= s.num_spheres) {
+                    continue; // last-lane mask, sphere.cpp:31-37,46-49
+                }
+                float lx = xs[k] - o[0];
+                float ly = ys[k] - o[1];
+                float lz = zs[k] - o[2];
+                float distSq = dot3(lx, ly, lz, lx, ly, lz);
+                float radSq = rs[k];
+                if (!(distSq > radSq)) {
+                    continue;
+                }
+                float tca = dot3(lx, ly, lz, d[0], d[1], d[2]);
+                float tcaSq = tca * tca;
+                float d2 = distSq - tcaSq;
+                if (!(d2 < radSq)) {
+                    continue;
+                }
+                float thcSq = radSq - d2;
+                float thc = sqrtf(thcSq);
+                float t0 = tca - thc;
+                float t1 = tca + thc;
+                if (!(t0 >= 0.0f && t1 >= 0.0f)) {
+                    continue;
+                }
+                float tm = t0 < t1 ? t0 : t1; // _mm256_min_ps operand rule
+                if (tm < minDist) {
+                    minDist = tm;
+                    minIdx = j;
+                }
+            }
+        }
+        if (minDist < recordT) {
+            recordT = minDist;
+            closest = i * kLane + minIdx;
+            if (any) {
+                break;
+            }
+        }
+    }
+    if (closest == DODRT_MISS) {
+        return false;
+    }
+    hit.t = recordT;
+    hit.prim = (DODRT_KIND_SPHERE << DODRT_KIND_SHIFT) | closest;
+    hit.u = hit.v = 0.0f;
+    return true;
+}
+
+// Plane::intersect_impl, plane.cpp:27-139
+__device__ __forceinline__ bool plane_query(const DeviceScene &s, const float o[3], const float d[3], float clip,
+                                            Hit &hit)
+{
+    float minT = clip;
+    uint32_t closest = DODRT_MISS;
+    const float eps = s.epsilon;
+    const uint32_t numLanes = (s.num_planes + kLane - 1) / kLane;
+    for (uint32_t i = 0; i < numLanes; i++) {
+        const float *lane = s.plane_lanes + (size_t)i * 6 * kLane;
+#pragma unroll
+        for (int j = 0; j < kLane; j++) {
+            float px = __ldg(lane + 0 * kLane + j), py = __ldg(lane + 1 * kLane + j), pz = __ldg(lane + 2 * kLane + j);
+            float nx = __ldg(lane + 3 * kLane + j), ny = __ldg(lane + 4 * kLane + j), nz = __ldg(lane + 5 * kLane + j);
+            float denom = dot3(d[0], d[1], d[2], nx, ny, nz);
+            if (!(fabsf(denom) > eps)) {
+                continue;
+            }
+            float vx = px - o[0], vy = py - o[1], vz = pz - o[2];
+            float num = dot3(vx, vy, vz, nx, ny, nz);
+            float t = num / denom;
+            if (!(t > eps)) {
+                continue;
+            }
+            if (t < minT) {
+                minT = t;
+                closest = i * kLane + j;
+            }
+        }
+    }
+    if (closest == DODRT_MISS) {
+        return false;
+    }
+    hit.t = minT;
+    hit.prim = (DODRT_KIND_PLANE << DODRT_KIND_SHIFT) | closest;
+    hit.u = hit.v = 0.0f;
+    return true;
+}
+
+// minNonNegative, cylinder.cpp:8-26
+__device__ __forceinline__ float min_non_negative(float a, float b)
+{
+    if (a < 0 && b < 0) {
+        return __int_as_float(0x7f800000);
+    } else if (a < 0) {
+        return b;
+    } else if (b < 0) {
+        return a;
+    }
+    return fminf(a, b);
+}
+
+// Cylinder::intersect_cylinder_body, cylinder.cpp:76-118.  The two roots go through double because
+// the reference calls ::sqrt(double) on a float (cylinder.cpp:92-93).
+__device__ __forceinline__ bool cylinder_body(const dodrt_cylinder &c, const float o[3], const float d[3], float eps,
+                                              float &tOut)
+{
+    float dpx = o[0] - c.base[0], dpy = o[1] - c.base[1], dpz = o[2] - c.base[2];
+    float k = dot3(d[0], d[1], d[2], c.axis[0], c.axis[1], c.axis[2]);
+    float vx = d[0] - k * c.axis[0], vy = d[1] - k * c.axis[1], vz = d[2] - k * c.axis[2];
+    float m = dot3(dpx, dpy, dpz, c.axis[0], c.axis[1], c.axis[2]);
+    float rx = dpx - m * c.axis[0], ry = dpy - m * c.axis[1], rz = dpz - m * c.axis[2];
+    float a = dot3(vx, vy, vz, vx, vy, vz);
+    float b = 2.0f * dot3(vx, vy, vz, rx, ry, rz);
+    float cc = dot3(rx, ry, rz, rx, ry, rz) - c.radius_sq;
+    float disc = (b * b) - (4.0f * a * cc);
+    if (disc < eps) {
+        return false;
+    }
+    double sq = sqrt((double)disc);
+    double den = (double)(2.0f * a);
+    float tSub = (float)(__ddiv_rn(__dsub_rn((double)(-b), sq), den));
+    float tAdd = (float)(__ddiv_rn(__dadd_rn((double)(-b), sq), den));
+    float t = min_non_negative(tSub, tAdd);
+    if (t == __int_as_float(0x7f800000)) {
+        return false;
+    }
+    float cx = (o[0] + d[0] * t) - c.base[0];
+    float cy = (o[1] + d[1] * t) - c.base[1];
+    float cz = (o[2] + d[2] * t) - c.base[2];
+    float f = dot3(cx, cy, cz, c.axis[0], c.axis[1], c.axis[2]);
+    if (f < 0.f || f > c.height) {
+        return false;
+    }
+    tOut = t;
+    return true;
+}
+
+// Cylinder::intersect_cylinder_disc, cylinder.cpp:120-152 (minT is the ORIGINAL clip, cylinder.cpp:122)
+__device__ __forceinline__ bool cylinder_disc(const dodrt_cylinder &c, const float o[3], const float d[3], float eps,
+                                              float offset, float clip, float &tOut)
+{
+    float px = c.base[0] + c.axis[0] * offset;
+    float py = c.base[1] + c.axis[1] * offset;
+    float pz = c.base[2] + c.axis[2] * offset;
+    float denom = dot3(d[0], d[1], d[2], c.axis[0], c.axis[1], c.axis[2]);
+    if (fabsf(denom) < eps) {
+        return false;
+    }
+    float vx = px - o[0], vy = py - o[1], vz = pz - o[2];
+    float tnum = dot3(vx, vy, vz, c.axis[0], c.axis[1], c.axis[2]);
+    float t = tnum / denom;
+    if (t < eps || t > clip) {
+        return false;
+    }
+    float hx = o[0] + d[0] * t, hy = o[1] + d[1] * t, hz = o[2] + d[2] * t;
+    float wx = hx - px, wy = hy - py, wz = hz - pz;
+    if (dot3(wx, wy, wz, wx, wy, wz) > c.radius_sq) {
+        return false;
+    }
+    tOut = t;
+    return true;
+}
+
+// Cylinder::intersect_non_vectorized, cylinder.cpp:155-210
+__device__ __forceinline__ bool cylinder_query(const DeviceScene &s, const float o[3], const float d[3], float clip,
+                                               Hit &hit)
+{
+    uint32_t minIdx = DODRT_MISS;
+    float tMin = clip;
+    for (uint32_t i = 0; i < s.num_cylinders; i++) {
+        const dodrt_cylinder c = s.cylinders[i];
+        float t;
+        if (cylinder_body(c, o, d, s.epsilon, t) && t < tMin) {
+            tMin = t;
+            minIdx = i;
+        }
+        if (cylinder_disc(c, o, d, s.epsilon, 0.0f, clip, t) && t < tMin) {
+            tMin = t;
+            minIdx = i;
+        }
+        if (cylinder_disc(c, o, d, s.epsilon, c.height, clip, t) && t < tMin) {
+            tMin = t;
+            minIdx = i;
+        }
+    }
+    if (minIdx == DODRT_MISS) {
+        return false;
+    }
+    hit.t = tMin;
+    hit.prim = (DODRT_KIND_CYLINDER << DODRT_KIND_SHIFT) | minIdx;
+    hit.u = hit.v = 0.0f;
+    return true;
+}
+
+// EXTENSION: renderable boxes with the slab arithmetic of box.cpp:33-53 (see include/dodrt.h)
+__device__ __forceinline__ bool box_query(const DeviceScene &s, const float o[3], const float d[3], bool any,
+                                          float clip, Hit &hit)
+{
+    const float inv[3] = {1.0f / d[0], 1.0f / d[1], 1.0f / d[2]};
+    float recordT = clip;
+    uint32_t closest = DODRT_MISS;
+    const uint32_t numLanes = (s.num_boxes + kLane - 1) / kLane;
+    for (uint32_t i = 0; i < numLanes; i++) {
+        const float *lane = s.box_lanes + (size_t)i * 6 * kLane;
+        bool laneHit = false;
+#pragma unroll
+        for (int j = 0; j < kLane; j++) {
+            if (i * kLane + j >= s.num_boxes) {
+                continue;
+            }
+            float bmin[3] = {__ldg(lane + 0 * kLane + j), __ldg(lane + 1 * kLane + j), __ldg(lane + 2 * kLane + j)};
+            float bmax[3] = {__ldg(lane + 3 * kLane + j), __ldg(lane + 4 * kLane + j), __ldg(lane + 5 * kLane + j)};
+            float tmin, tmax;
+            if (!slab(bmin, bmax, o, inv, clip, tmin, tmax)) {
+                continue;
+            }
+            if (tmin > 0.0f && tmin < recordT) {
+                recordT = tmin;
+                closest = i * kLane + j;
+                laneHit = true;
+            }
+        }
+        if (laneHit && any) {
+            break;
+        }
+    }
+    if (closest == DODRT_MISS) {
+        return false;
+    }
+    hit.t = recordT;
+    hit.prim = (DODRT_KIND_BOX << DODRT_KIND_SHIFT) | closest;
+    hit.u = hit.v = 0.0f;
+    return true;
+}
+
+// Primary ray direction, main.cpp:304: glm::normalize(v) = v * (1 / sqrt(dot(v,v)))
+__device__ __forceinline__ void primary_dir(float vx, float vy, float d[3])
+{
+    const float vz = 1.0f;
+    float inv = 1.0f / sqrtf(dot3(vx, vy, vz, vx, vy, vz));
+    d[0] = vx * inv;
+    d[1] = vy * inv;
+    d[2] = vz * inv;
+}
+
+// canSeeLight's ray, main.cpp:184-196, from hitPoint = o + d*t (triangle.cpp:170 / sphere.cpp:156)
+__device__ __forceinline__ void shadow_ray(const float o[3], const float d[3], float t, const float light[3],
+                                           float so[3], float sd[3], float &clip)
+{
+    float p[3];
+#pragma unroll
+    for (int k = 0; k < 3; k++) {
+        float m = d[k] * t;
+        p[k] = o[k] + m;
+    }
+    float lx = light[0] - p[0], ly = light[1] - p[1], lz = light[2] - p[2];
+    float dist = sqrtf(dot3(lx, ly, lz, lx, ly, lz));
+    lx = lx / dist;
+    ly = ly / dist;
+    lz = lz / dist;
+    sd[0] = lx;
+    sd[1] = ly;
+    sd[2] = lz;
+    so[0] = p[0] + lx * 0.01f;
+    so[1] = p[1] + ly * 0.01f;
+    so[2] = p[2] + lz * 0.01f;
+    clip = dist;
+}
+
+} // namespace dodrt

@@ -1,0 +1,44 @@
+// dodrt_kernels.cuh -- launch interface between the C ABI (dodrt_api.cu) and the kernels.
+#pragma once
+#include "dodrt_device.cuh"
+
+namespace dodrt {
+
+enum TraceMode : int {
+    kModeRays = 0,    // explicit dodrt_ray batch            (dodrt_intersect*)
+    kModePrimary = 1, // in-kernel primary ray generation     (dodrt_trace_primary*)
+    kModeShadow = 2,  // in-kernel shadow ray generation      (dodrt_trace_shadow*)
+};
+
+struct TraceParams {
+    DeviceScene scene;
+    uint32_t classes;
+    // kModeRays
+    const dodrt_ray *rays;
+    // all modes: number of work items (rays, or result slots of the frame incl. edge padding)
+    uint64_t count;
+    // kModeRays/kModePrimary: output ; kModeShadow: input
+    dodrt_hit *hits;
+    // frame modes
+    dodrt_frame frame;
+    uint32_t tiles_x;
+    const float *xs, *ys;
+    float light[3];
+    uint8_t *visible;
+    // dynamic work distribution: one counter per launch, zeroed on the stream before the launch
+    unsigned long long *counter;
+};
+
+struct LaunchConfig {
+    int grid;
+    int block;
+};
+
+// Occupancy-derived persistent launch shape for the given device (cached by the caller).
+cudaError_t trace_launch_config(int device, TraceMode mode, LaunchConfig *cfg);
+cudaError_t launch_trace(TraceMode mode, const TraceParams &p, const LaunchConfig &cfg, cudaStream_t stream);
+
+// Upload helper: reference lanes (288 B, SoA of 8) -> per-triangle 48-B records with AB/AC.
+cudaError_t launch_repack_triangles(const float *d_lanes, uint32_t num_lanes, float4 *d_tris, cudaStream_t stream);
+
+} // namespace dodrt

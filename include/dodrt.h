@@ -1,0 +1,188 @@
+/* dodrt.h -- C ABI of the B200-native ray-query path (libdodrt_cuda.so).
+ *
+ * This is the drop-in boundary for the hot path of AVassilev98/dod_raytracer: kd-tree traversal
+ * (src/accelerators/kdtree.cpp) driving ray-triangle, ray-sphere and ray-box intersection
+ * (src/shapes) for primary and shadow rays.  The reference has no process, device or FFI boundary
+ * (it is one C++ executable); the entry points below are the batched mirror of the C++ interface
+ * the reference's render loop calls, and each one cites the reference interface it replaces.
+ * Plain pointers and sizes only; no C++ or torch types.  INTEGRATION.md shows the adapter a
+ * reference maintainer adds on the C++ side.
+ *
+ * Conventions
+ *   - every function returns 0 on success, a negative DODRT_E_* code otherwise, and never throws;
+ *     dodrt_last_error() returns a thread-local description of the last failure.
+ *   - the reference's bool hit/miss (base_shape.h:23) is carried in dodrt_hit.prim: DODRT_MISS = miss.
+ *   - arithmetic is fp32, round-to-nearest, un-fused, IEEE div/sqrt, in the reference's operation
+ *     order, so t/u/v are bit-identical to the reference CPU path and prim ids are identical.
+ *   - there is NO CPU fallback: without a usable CUDA device every call fails with DODRT_E_CUDA.
+ *   - a scene is immutable while queries run on it (like the reference: main.cpp:364-368 then
+ *     main.cpp:371-394); queries on one scene may be issued from several host threads.
+ */
+#ifndef DODRT_H
+#define DODRT_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DODRT_ABI_VERSION 1
+
+#if defined(__GNUC__)
+#define DODRT_API __attribute__((visibility("default")))
+#else
+#define DODRT_API
+#endif
+
+/* status codes */
+#define DODRT_OK 0
+#define DODRT_E_INVALID (-1) /* bad argument */
+#define DODRT_E_CUDA (-2)    /* CUDA runtime error (message has the cudaError string) */
+#define DODRT_E_LIMIT (-3)   /* scene exceeds a compiled-in limit (e.g. kd-tree depth) */
+#define DODRT_E_NOMEM (-4)
+
+/* primitive id encoding in dodrt_hit.prim: kind << 29 | id */
+#define DODRT_MISS 0xFFFFFFFFu
+#define DODRT_KIND_SHIFT 29
+#define DODRT_KIND_TRIANGLE 0u /* id = (laneIdx * 8 + slot) in RE-ORDERED lane space, triangle.cpp:136 */
+#define DODRT_KIND_SPHERE 1u   /* id = creation index, sphere.cpp:137 */
+#define DODRT_KIND_PLANE 2u    /* id = creation index, plane.cpp:110 */
+#define DODRT_KIND_CYLINDER 3u /* id = creation index, cylinder.cpp:180 */
+#define DODRT_KIND_BOX 4u      /* extension, see dodrt_scene_set_boxes */
+
+/* shape classes a query visits, in the reference's fixed order (main.cpp:314-321):
+ * Sphere -> [Box] -> Plane -> Cylinder -> KDTree, each clipped by the running record.t */
+#define DODRT_CLS_SPHERE 1u
+#define DODRT_CLS_PLANE 2u
+#define DODRT_CLS_CYLINDER 4u
+#define DODRT_CLS_TREE 8u
+#define DODRT_CLS_BOX 16u
+#define DODRT_CLS_ALL 31u
+
+#define DODRT_RAY_ANY 1u /* _Intersect::returnOnAny, base_shape.h:12 */
+
+/* One query = the reference's `_Intersect` (base_shape.h:8-15) without the HitRecord reference. */
+typedef struct dodrt_ray {
+    float o[3];     /* rayOrigin */
+    float d[3];     /* rayDir (the reference passes normalised directions; not required) */
+    float clip;     /* clippingDistance; +inf for an unclipped closest-hit query */
+    uint32_t flags; /* DODRT_RAY_ANY */
+} dodrt_ray;
+
+/* The part of the reference's HitRecord (hitrecord.h:4-10) that the intersect path produces, plus
+ * the primitive id the reference keeps in a local (triangle.cpp:37, sphere.cpp:29).  hitPoint is
+ * o + d*t and hitNormal/color follow from (prim,u,v); they are rebuilt by the shading stage.
+ * For a DODRT_RAY_ANY query only hit/miss is defined: prim is 0 on a hit, DODRT_MISS otherwise. */
+typedef struct dodrt_hit {
+    float t;       /* record.t; the query's clip on a miss */
+    uint32_t prim; /* kind << 29 | id, or DODRT_MISS */
+    float u, v;    /* triangle barycentrics (triangle.cpp:137: bary = (1-(u+v), u, v)); 0 otherwise */
+} dodrt_hit;
+
+/* Cylinder as the reference stores it after construction (cylinder.h:33-36, cylinder.cpp:223-229). */
+typedef struct dodrt_cylinder {
+    float base[3];
+    float axis[3]; /* normalised */
+    float radius_sq;
+    float height;
+} dodrt_cylinder;
+
+/* Frame description for the fused passes.  Pixels are grouped into tiles of tile_w x tile_h
+ * (multiples of 8 and 4); tile k of the row-major tile grid belongs to this call iff
+ * k >= first_tile and (k - first_tile) % tile_stride == 0.  One GPU: first_tile 0, tile_stride 1.
+ * N GPUs (image-tile split, scene replicated): rank r passes first_tile = r, tile_stride = N.
+ * With compact = 0 results are indexed by pixel (row * width + col) in a full-frame buffer (pixels
+ * of other ranks' tiles are left untouched); with compact = 1 they are packed in this call's own
+ * order: slot = local_tile * tile_w * tile_h + in-tile index (see dodrt_frame_local_pixels and
+ * dodrt_frame_pixel_map), padded slots of partial edge tiles hold DODRT_MISS / 0. */
+typedef struct dodrt_frame {
+    uint32_t width, height;
+    uint32_t tile_w, tile_h;
+    uint32_t first_tile, tile_stride;
+    uint32_t classes; /* DODRT_CLS_* mask */
+    uint32_t compact;
+    float origin[3]; /* camera position, main.cpp:275 = (0,0,-4.9) */
+} dodrt_frame;
+
+typedef struct dodrt_scene dodrt_scene; /* opaque; owns one replica of the scene in one GPU's HBM */
+
+/* ---- library ------------------------------------------------------------------------------- */
+DODRT_API int dodrt_abi_version(void);
+DODRT_API const char *dodrt_last_error(void);
+DODRT_API int dodrt_device_count(int *count);
+
+/* ---- scene registration ---------------------------------------------------------------------
+ * Replaces the reference's process-global registration (Sphere::create sphere.h:27, Plane::create
+ * plane.h:25, Cylinder::create cylinder.h:29, Mesh::Create mesh.h:24 -> Triangle::create
+ * triangle.h:56) followed by KDTree::buildTree() (kdtree.h:12).  The host side keeps building the
+ * scene exactly as the reference does; these calls copy the finished arrays, in the reference's own
+ * layouts, into the GPU (the caller keeps ownership of the host memory). */
+DODRT_API int dodrt_scene_create(int device, dodrt_scene **scene);
+DODRT_API int dodrt_scene_destroy(dodrt_scene *scene);
+
+/* nodes: KDTree::m_nodes (kdtree.h:16-48,63), 8 bytes each, DFS pre-order, left child = node+1.
+ * tri_lanes: Triangle::m_triangleLanes AFTER Triangle::reorderLanesByIndices (triangle.h:33-44,
+ * triangle.cpp:349-367), 288 bytes each: Ax[8] Ay[8] Az[8] Bx[8] .. Cz[8]; padding slots all-zero.
+ * bounds: KDTree::m_bounds (kdtree.h:67), min xyz then max xyz. */
+DODRT_API int dodrt_scene_set_kdtree(dodrt_scene *scene, const uint64_t *nodes, uint32_t num_nodes, const float *tri_lanes,
+                           uint32_t num_tri_lanes, const float bounds[6]);
+/* sphere lanes as sphere.cpp:12-19: x[8] y[8] z[8] radiusSq[8], 128 bytes per lane, ceil(n/8) lanes */
+DODRT_API int dodrt_scene_set_spheres(dodrt_scene *scene, const float *sphere_lanes, uint32_t num_spheres);
+/* plane lanes as plane.cpp:13-20: px[8] py[8] pz[8] nx[8] ny[8] nz[8]; epsilon = Config::Epsilon */
+DODRT_API int dodrt_scene_set_planes(dodrt_scene *scene, const float *plane_lanes, uint32_t num_planes);
+DODRT_API int dodrt_scene_set_cylinders(dodrt_scene *scene, const dodrt_cylinder *cylinders, uint32_t num_cylinders);
+/* EXTENSION (BASELINE.json config 4; the reference's box.h is only the kd-tree bounds helper):
+ * renderable axis-aligned boxes, lanes minx[8] miny[8] minz[8] maxx[8] maxy[8] maxz[8], tested with
+ * the slab arithmetic of AxisAlignedBoundingBox::intersect (box.cpp:33-53); hit distance = entry
+ * distance, accepted when it is > 0 and < the running record.t. */
+DODRT_API int dodrt_scene_set_boxes(dodrt_scene *scene, const float *box_lanes, uint32_t num_boxes);
+/* Config::Epsilon (config.h:9), used by the plane and cylinder tests; default 1e-4 */
+DODRT_API int dodrt_scene_set_epsilon(dodrt_scene *scene, float epsilon);
+
+/* ---- queries: host buffers (copies in and out are part of the call) --------------------------
+ * dodrt_intersect is the batch form of `bool KDTree::intersect(_Intersect&) const` (kdtree.h:13) and
+ * `static bool BaseShape<D>::intersect(_Intersect&)` (base_shape.h:23) chained as in
+ * main.cpp:314-321 (closest) / main.cpp:198-217 (DODRT_RAY_ANY): hits[i] answers rays[i]. */
+DODRT_API int dodrt_intersect(dodrt_scene *scene, const dodrt_ray *rays, uint64_t num_rays, uint32_t classes, dodrt_hit *hits);
+
+/* dodrt_trace_primary replaces the primary-ray half of rayTrace (main.cpp:273-321 with k = 0):
+ * dir = normalize((xs[col], ys[row], 1)) (main.cpp:304; xs/ys are the accumulated raster tables of
+ * main.cpp:276-279,342-345, width resp. height floats), closest-hit chain from frame->origin. */
+DODRT_API int dodrt_trace_primary(dodrt_scene *scene, const dodrt_frame *frame, const float *xs, const float *ys,
+                        dodrt_hit *hits);
+/* dodrt_trace_shadow replaces canSeeLight (main.cpp:182-219) for every pixel with a primary hit:
+ * visible[i] = 1 iff hits[i] is a hit and no shape blocks hitPoint -> light; 0 otherwise. */
+DODRT_API int dodrt_trace_shadow(dodrt_scene *scene, const dodrt_frame *frame, const float *xs, const float *ys,
+                       const dodrt_hit *hits, const float light[3], uint8_t *visible);
+/* primary + one shadow pass per light without the intermediate round trip through the host;
+ * visible is [num_lights][slots]. */
+DODRT_API int dodrt_trace_frame(dodrt_scene *scene, const dodrt_frame *frame, const float *xs, const float *ys,
+                      const float *lights /* num_lights x 3 */, uint32_t num_lights, dodrt_hit *hits,
+                      uint8_t *visible);
+
+/* ---- queries: device-resident buffers (pointers in the scene's GPU memory, asynchronous on
+ * `stream`, a cudaStream_t passed as void*; NULL = the default stream).  Used when the caller keeps
+ * rays/hits on the GPU (next pipeline stage, NCCL gather, benchmarks). */
+DODRT_API int dodrt_intersect_device(dodrt_scene *scene, const dodrt_ray *d_rays, uint64_t num_rays, uint32_t classes,
+                           dodrt_hit *d_hits, void *stream);
+DODRT_API int dodrt_trace_primary_device(dodrt_scene *scene, const dodrt_frame *frame, const float *d_xs, const float *d_ys,
+                               dodrt_hit *d_hits, void *stream);
+DODRT_API int dodrt_trace_shadow_device(dodrt_scene *scene, const dodrt_frame *frame, const float *d_xs, const float *d_ys,
+                              const dodrt_hit *d_hits, const float light[3], uint8_t *d_visible, void *stream);
+
+/* ---- frame helpers (host only, no GPU work) -------------------------------------------------- */
+/* number of result slots a call with this frame description writes when compact = 1 */
+DODRT_API int dodrt_frame_local_pixels(const dodrt_frame *frame, uint64_t *slots);
+/* pixel_of_slot[s] = row * width + col of compact slot s, or 0xFFFFFFFF for a padded slot */
+DODRT_API int dodrt_frame_pixel_map(const dodrt_frame *frame, uint32_t *pixel_of_slot, uint64_t slots);
+
+/* ---- instrumentation ------------------------------------------------------------------------- */
+/* kernels launched by this library on behalf of this scene since creation */
+DODRT_API int dodrt_scene_launch_count(dodrt_scene *scene, uint64_t *launches);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DODRT_H */

@@ -1,0 +1,134 @@
+"""Deterministic test scenes and ray sets shared by the tests and tests/golden/make_golden.py."""
+from __future__ import annotations
+
+import os
+
+import numpy as np
+
+from oracle_api import RAY_DT, Scene, reference_cylinder, reference_planes
+
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+LIGHT0 = np.array([0.0, 0.0, -2.0], np.float32)  # lights[0], main.cpp:284
+
+
+def lcg_uniform(seed: int, n: int) -> np.ndarray:
+    """n fp32 values in [0,1): x <- 1664525 x + 1013904223 (mod 2^32), value = (x >> 8) / 2^24."""
+    vals = np.empty(n, np.uint32)
+    x = seed & 0xFFFFFFFF
+    for i in range(n):
+        x = (1664525 * x + 1013904223) & 0xFFFFFFFF
+        vals[i] = x >> 8
+    return vals.astype(np.float32) / np.float32(16777216.0)  # both exact in fp32
+
+
+def analytic_scene_arrays(seed: int = 4, count: int = 10000):
+    """BASELINE.json config 4 law: centres uniform in [-4.5,4.5]^3, radius / half-extent uniform in
+    [0.03,0.12].  Returns (spheres [N,4] x y z r, boxes [N,6] min xyz max xyz)."""
+    u = lcg_uniform(seed, count * 8).reshape(count, 8)
+    nine, lo, span = np.float32(9.0), np.float32(4.5), np.float32(0.09)
+    sc = u[:, 0:3] * nine - lo
+    sr = u[:, 3] * span + np.float32(0.03)
+    bc = u[:, 4:7] * nine - lo
+    bh = (u[:, 7] * span + np.float32(0.03))[:, None]
+    spheres = np.concatenate([sc, sr[:, None]], axis=1).astype(np.float32)
+    boxes = np.concatenate([bc - bh, bc + bh], axis=1).astype(np.float32)
+    return spheres, boxes
+
+
+def load_teapot_arrays():
+    """The flattened teapot scene exactly as the reference builds it (fixture made by make_golden.py)."""
+    z = np.load(os.path.join(GOLDEN, "teapot_scene.npz"))
+    lanes = z["orig_lanes"][z["prim_nums"]]  # Triangle::reorderLanesByIndices, triangle.cpp:349-367
+    return dict(nodes=z["nodes"], tri_lanes=np.ascontiguousarray(lanes), bounds=z["bounds"], prim_nums=z["prim_nums"],
+                spheres=z["spheres"], max_depth=int(z["max_depth"]))
+
+
+def teapot_scene(full: bool = True) -> Scene:
+    """Teapot kd-tree + (if full) the reference's 16 srand(1) spheres, 6 planes and the cylinder."""
+    a = load_teapot_arrays()
+    if not full:
+        return Scene(a["nodes"], a["tri_lanes"], a["bounds"])
+    return Scene(a["nodes"], a["tri_lanes"], a["bounds"], spheres=a["spheres"][:, :4], planes=reference_planes(),
+                 cylinders=reference_cylinder())
+
+
+def make_rays(o, d, clip=np.inf, flags=0) -> np.ndarray:
+    o = np.asarray(o, np.float32).reshape(-1, 3)
+    d = np.asarray(d, np.float32).reshape(-1, 3)
+    n = max(len(o), len(d))
+    rays = np.zeros(n, RAY_DT)
+    rays["o"], rays["d"] = o, d
+    rays["clip"] = clip
+    rays["flags"] = flags
+    return rays
+
+
+def edge_rays(nodes: np.ndarray, bounds: np.ndarray) -> np.ndarray:
+    """Edge cases of SURVEY.md section 4: axis-parallel rays (inv = +-inf, NaN from 0*inf in the
+    slabs), origins exactly on split planes and on the bounds, origins inside the tree, clipped
+    queries (clip < tmin at entry), any-hit rays."""
+    w0 = (nodes & np.uint64(0xFFFFFFFF)).astype(np.uint32)
+    w1 = (nodes >> np.uint64(32)).astype(np.uint32)
+    interior = (w0 & 3) != 3
+    splits = w1[interior].view(np.float32)
+    axes = (w0[interior] & 3).astype(np.int64)
+    lo, hi = bounds[:3], bounds[3:]
+    ctr = (lo + hi) * np.float32(0.5)
+    rays = []
+    # axis-parallel grids through the bounds, both directions, from outside and from the centre planes
+    g = np.linspace(0.03, 0.97, 12, dtype=np.float32)
+    for ax in range(3):
+        a1, a2 = (ax + 1) % 3, (ax + 2) % 3
+        for s in (-1.0, 1.0):
+            for u in g:
+                for v in g:
+                    o = np.zeros(3, np.float32)
+                    o[a1] = lo[a1] + u * (hi[a1] - lo[a1])
+                    o[a2] = lo[a2] + v * (hi[a2] - lo[a2])
+                    d = np.zeros(3, np.float32)
+                    d[ax] = s
+                    for start in (lo[ax] - 1.0 if s > 0 else hi[ax] + 1.0, ctr[ax], lo[ax] if s > 0 else hi[ax]):
+                        o2 = o.copy()
+                        o2[ax] = start
+                        rays.append((o2, d.copy(), np.inf, 0))
+    # origins exactly on split planes, with zero / negative / positive direction along the split axis
+    rng = np.random.RandomState(7)
+    pick = rng.choice(len(splits), size=min(200, len(splits)), replace=False)
+    for k in pick:
+        ax = int(axes[k])
+        o = (lo + rng.rand(3).astype(np.float32) * (hi - lo)).astype(np.float32)
+        o[ax] = splits[k]
+        for comp in (0.0, -0.5, 0.5):
+            d = rng.randn(3).astype(np.float32)
+            d[ax] = comp
+            d /= np.float32(np.sqrt(np.float32((d * d).sum())))
+            rays.append((o.copy(), d, np.inf, 0))
+    # random rays from a shell around the tree towards points inside it, some clipped short,
+    # some any-hit with a finite clip
+    for i in range(1500):
+        p = (lo + rng.rand(3).astype(np.float32) * (hi - lo)).astype(np.float32)
+        o = (ctr + rng.randn(3).astype(np.float32) * np.float32(6.0)).astype(np.float32)
+        d = p - o
+        dist = np.float32(np.sqrt(np.float32((d * d).sum())))
+        d = (d / dist).astype(np.float32)
+        mode = i % 4
+        if mode == 0:
+            rays.append((o, d, np.inf, 0))
+        elif mode == 1:
+            rays.append((o, d, np.float32(dist * rng.rand()), 0))  # clipped closest-hit
+        elif mode == 2:
+            rays.append((o, d, dist, 1))  # any-hit to a point inside
+        else:
+            rays.append((p, -d, np.inf, 0))  # origin inside the bounds
+    out = np.zeros(len(rays), RAY_DT)
+    for i, (o, d, c, f) in enumerate(rays):
+        out[i]["o"], out[i]["d"], out[i]["clip"], out[i]["flags"] = o, d, c, f
+    return out
+
+
+def hit_points(rays: np.ndarray, t: np.ndarray) -> np.ndarray:
+    """hitPoint = o + d*t, mul then add in fp32 (triangle.cpp:170)."""
+    p = np.empty((len(rays), 3), np.float32)
+    for k in range(3):
+        p[:, k] = rays["o"][:, k] + (rays["d"][:, k] * t.astype(np.float32)).astype(np.float32)
+    return p

@@ -1,0 +1,192 @@
+"""GPU (-m gpu): the CUDA path, called through the C ABI, against the oracle restatement on the same
+inputs, against the committed reference fixtures, and -- when oracle/_ref travelled -- against the
+reference's own code.  Integer/ids bit-exact; fp32 t/u/v bit-exact (tolerance: 0 ulp)."""
+import hashlib
+
+import numpy as np
+import pytest
+
+from dod_raytracer_b200 import capi
+from gpu_util import assert_hits_equal, upload
+from oracle_api import (CLS_BOX, CLS_CYLINDER, CLS_PLANE, CLS_SPHERE, CLS_TREE, MISS, RAY_ANY, RefLib, Scene, have_ref,
+                        reference_cylinder, reference_planes)
+from scenes import (GOLDEN, LIGHT0, analytic_scene_arrays, hit_points, load_teapot_arrays, make_rays, teapot_scene)
+
+pytestmark = pytest.mark.gpu
+ALL = CLS_SPHERE | CLS_PLANE | CLS_CYLINDER | CLS_TREE
+CLASSES = {"tree": CLS_TREE, "all": ALL, "sphere_tree": CLS_SPHERE | CLS_TREE}
+
+
+def sha(a):
+    return hashlib.sha256(np.ascontiguousarray(a).tobytes()).hexdigest()
+
+
+@pytest.fixture(scope="module")
+def teapot():
+    scene = teapot_scene(full=True)
+    g = upload(scene)
+    yield scene, g
+    g.close()
+
+
+def test_explicit_ray_batches_match_oracle(teapot, oracle):
+    scene, g = teapot
+    rays = oracle.primary_rays(640, 360)
+    for cls in (CLS_TREE, CLS_SPHERE, CLS_PLANE, CLS_CYLINDER, ALL, CLS_SPHERE | CLS_TREE, CLS_PLANE | CLS_CYLINDER):
+        want = oracle.intersect(scene, rays, cls, nthreads=8)
+        got = g.intersect(rays, cls)
+        assert_hits_equal(got, want, what=f"classes={cls}")
+
+
+def test_full_1080p_frame_matches_reference_fixture(teapot):
+    """BASELINE.json config 1 geometry: teapot, 1920x1080, srand(1) spheres + planes + cylinder, light0.
+    Checksums of the complete hit / visibility arrays produced by the reference itself."""
+    _, g = teapot
+    z = np.load(f"{GOLDEN}/teapot_frame.npz")
+    w, h, step = int(z["width"]), int(z["height"]), int(z["step"])
+    sel = (np.arange(0, h, step)[:, None] * w + np.arange(0, w, step)[None, :]).ravel()
+    from oracle_api import Oracle
+    xs, ys = Oracle().ray_tables(w, h)
+    for name, cls in CLASSES.items():
+        frame = capi.Frame.make(w, h, classes=cls)
+        hits = g.trace_primary(frame, xs, ys)
+        assert_hits_equal(hits[sel], z[f"{name}_hits"], what=name)
+        assert int((hits["prim"] != MISS).sum()) == int(z[f"{name}_num_hits"])
+        assert sha(hits) == str(z[f"{name}_hits_sha"]), name
+        vis = g.trace_shadow(frame, xs, ys, hits, LIGHT0)
+        assert int(vis.sum()) == int(z[f"{name}_num_visible"])
+        assert sha(vis) == str(z[f"{name}_vis_sha"]), name
+        # fused primary + shadow call gives the same bytes
+        h2, v2 = g.trace_frame(frame, xs, ys, LIGHT0[None, :])
+        assert h2.tobytes() == hits.tobytes() and v2[0].tobytes() == vis.tobytes()
+
+
+def test_edge_case_rays_match_reference_fixture(teapot):
+    _, g = teapot
+    z = np.load(f"{GOLDEN}/teapot_edge.npz")
+    rays = z["rays"]
+    for name, cls in (("tree", CLS_TREE), ("all", ALL)):
+        assert_hits_equal(g.intersect(rays, cls), z[name], rays=rays, what=name)
+
+
+def test_random_rays_with_clips_and_any_hit(teapot, oracle):
+    scene, g = teapot
+    rng = np.random.RandomState(5)
+    n = 200000
+    o = (rng.rand(n, 3).astype(np.float32) - np.float32(0.5)) * np.float32(9.0)
+    d = rng.randn(n, 3).astype(np.float32)
+    d /= np.sqrt((d * d).sum(axis=1, dtype=np.float32))[:, None].astype(np.float32)
+    rays = make_rays(o, d)
+    rays["clip"][::3] = rng.rand(len(rays["clip"][::3])).astype(np.float32) * 8
+    rays["flags"][1::5] = RAY_ANY
+    for cls in (ALL, CLS_TREE):
+        want = oracle.intersect(scene, rays, cls, nthreads=8)
+        assert_hits_equal(g.intersect(rays, cls), want, rays=rays, what=f"random classes={cls}")
+
+
+def test_analytic_spheres_and_boxes(oracle):
+    z = np.load(f"{GOLDEN}/analytic10k.npz")
+    spheres, boxes = analytic_scene_arrays(4, 10000)
+    scene = Scene(spheres=spheres, boxes=boxes)
+    w, h = int(z["width"]), int(z["height"])
+    xs, ys = oracle.ray_tables(w, h)
+    with upload(scene) as g:
+        hits = g.trace_primary(capi.Frame.make(w, h, classes=CLS_SPHERE), xs, ys)
+        assert_hits_equal(hits, z["sphere_hits"], what="10k spheres")
+        vis = g.trace_shadow(capi.Frame.make(w, h, classes=CLS_SPHERE), xs, ys, hits, LIGHT0)
+        assert vis.tobytes() == z["sphere_vis"].tobytes()
+        bh = g.trace_primary(capi.Frame.make(w, h, classes=CLS_SPHERE | CLS_BOX), xs, ys)
+        assert_hits_equal(bh, z["sphere_box_hits_oracle"], what="spheres+boxes")
+    # partial last lane: 10 spheres, 3 boxes
+    small = Scene(spheres=spheres[:10], boxes=boxes[:3])
+    rays = oracle.primary_rays(96, 54)
+    with upload(small) as g:
+        assert_hits_equal(g.intersect(rays, CLS_SPHERE | CLS_BOX), oracle.intersect(small, rays, CLS_SPHERE | CLS_BOX))
+
+
+def test_tile_split_is_byte_identical_to_single_gpu(teapot, oracle):
+    """image-tile split: N ranks' compact results re-assembled == the one-GPU frame (no cross-tile math)"""
+    _, g = teapot
+    w, h = 500, 277  # not a multiple of the tile size: partial edge tiles
+    xs, ys = oracle.ray_tables(w, h)
+    full = g.trace_primary(capi.Frame.make(w, h, classes=ALL), xs, ys)
+    fvis = g.trace_shadow(capi.Frame.make(w, h, classes=ALL), xs, ys, full, LIGHT0)
+    for world, tile in ((2, (32, 32)), (3, (16, 8)), (8, (64, 16))):
+        hits = np.zeros(w * h, capi.HIT_DT)
+        vis = np.zeros(w * h, np.uint8)
+        for rank in range(world):
+            f = capi.Frame.make(w, h, classes=ALL, tile=tile, first_tile=rank, tile_stride=world, compact=1)
+            m = capi.frame_pixel_map(f)
+            lh, lv = g.trace_frame(f, xs, ys, LIGHT0[None, :])
+            ok = m != 0xFFFFFFFF
+            assert (lh["prim"][~ok] == MISS).all() and (lv[0][~ok] == 0).all()
+            hits[m[ok]] = lh[ok]
+            vis[m[ok]] = lv[0][ok]
+        assert hits.tobytes() == full.tobytes() and vis.tobytes() == fvis.tobytes()
+
+
+def test_device_resident_entry_points(teapot, oracle):
+    import torch
+    scene, g = teapot
+    w, h = 320, 180
+    rays = oracle.primary_rays(w, h)
+    want = oracle.intersect(scene, rays, ALL, nthreads=8)
+    dev = torch.device("cuda:0")
+    d_rays = torch.from_numpy(rays.view(np.uint8).reshape(-1, 32)).to(dev)
+    d_hits = torch.empty((len(rays), 16), dtype=torch.uint8, device=dev)
+    stream = torch.cuda.current_stream().cuda_stream
+    before = g.launch_count()
+    g.intersect_device(d_rays.data_ptr(), len(rays), ALL, d_hits.data_ptr(), stream)
+    torch.cuda.synchronize()
+    assert g.launch_count() == before + 1
+    assert_hits_equal(d_hits.cpu().numpy().reshape(-1).view(capi.HIT_DT), want)
+    xs, ys = oracle.ray_tables(w, h)
+    d_xs, d_ys = torch.from_numpy(xs).to(dev), torch.from_numpy(ys).to(dev)
+    d_hits.zero_()
+    frame = capi.Frame.make(w, h, classes=ALL)
+    g.trace_primary_device(frame, d_xs.data_ptr(), d_ys.data_ptr(), d_hits.data_ptr(), stream)
+    d_vis = torch.zeros(w * h, dtype=torch.uint8, device=dev)
+    g.trace_shadow_device(frame, d_xs.data_ptr(), d_ys.data_ptr(), d_hits.data_ptr(), LIGHT0, d_vis.data_ptr(), stream)
+    torch.cuda.synchronize()
+    got = d_hits.cpu().numpy().reshape(-1).view(capi.HIT_DT)
+    assert_hits_equal(got, want)
+    assert d_vis.cpu().numpy().tobytes() == oracle.trace_shadow(scene, w, h, ALL, want, LIGHT0, nthreads=8).tobytes()
+
+
+def test_empty_inputs_and_empty_tree(oracle):
+    with capi.Scene(0) as g:
+        rays = oracle.primary_rays(16, 8)
+        hits = g.intersect(rays, ALL)  # nothing registered: everything misses
+        assert (hits["prim"] == MISS).all() and np.isinf(hits["t"]).all()
+        assert len(g.intersect(rays[:0], ALL)) == 0
+        # the reference's tree for a missing mesh: one empty leaf (mesh.cpp:17-21, kdtree.cpp:106-110)
+        g.set_kdtree(np.array([3], np.uint64), np.zeros((0, 72), np.float32), np.array([np.inf] * 3 + [-np.inf] * 3))
+        assert (g.intersect(rays, CLS_TREE)["prim"] == MISS).all()
+        with pytest.raises(capi.DodrtError):  # leaf pointing past the lane array
+            g.set_kdtree(np.array([3 | (2 << 2)], np.uint64), np.zeros((1, 72), np.float32), np.zeros(6))
+
+
+@pytest.mark.skipif(not have_ref(), reason="oracle/_ref not present")
+def test_against_the_reference_code_directly():
+    """GPU vs the reference's own translation units (no restatement in between)."""
+    import os
+    ref = RefLib()
+    w, h = 480, 270
+    ref.set_config(w, h)
+    ref.add_reference_spheres(1, 16)
+    ref.add_reference_planes()
+    ref.add_reference_cylinder()
+    ref.add_mesh(os.path.join(GOLDEN, "teapot.dodm"))
+    ref.build_tree()
+    nodes, lanes, prim, bounds = ref.export_tree()
+    scene = Scene(nodes, lanes, bounds, spheres=ref.export_spheres()[:, :4], planes=reference_planes(),
+                  cylinders=reference_cylinder())
+    rays = ref.primary_rays(w, h)
+    with upload(scene) as g:
+        for cls in (CLS_TREE, ALL):
+            want = ref.intersect(rays, cls, 8)
+            got = g.intersect(rays, cls)
+            assert_hits_equal(got, want, what=f"vs reference classes={cls}")
+            pts = hit_points(rays, want["t"])
+            sr = ref.shadow_rays(pts, LIGHT0)
+            assert (g.intersect(sr, cls)["prim"] == ref.intersect(sr, cls, 8)["prim"]).all()
