@@ -34,7 +34,7 @@ EXPORTED_SYMBOLS = [
     "dodrt_scene_set_planes", "dodrt_scene_set_cylinders", "dodrt_scene_set_boxes", "dodrt_scene_set_epsilon",
     "dodrt_intersect", "dodrt_trace_primary", "dodrt_trace_shadow", "dodrt_trace_frame",
     "dodrt_intersect_device", "dodrt_trace_primary_device", "dodrt_trace_shadow_device",
-    "dodrt_frame_local_pixels", "dodrt_frame_pixel_map", "dodrt_scene_launch_count",
+    "dodrt_frame_assemble_device", "dodrt_frame_local_pixels", "dodrt_frame_pixel_map", "dodrt_scene_launch_count",
 ]
 
 
@@ -232,6 +232,13 @@ class Scene:
         _check(self._lib.dodrt_trace_shadow_device(self._h, C.byref(frame), C.c_void_p(d_xs), C.c_void_p(d_ys),
                                                    C.c_void_p(d_hits), _ptr(light), C.c_void_p(d_visible),
                                                    C.c_void_p(stream)))
+
+    def frame_assemble_device(self, frame: Frame, d_compact_hits: int, d_compact_vis: int, slots_per_rank: int,
+                              d_hits_out: int, d_vis_out: int, stream: int = 0):
+        _check(self._lib.dodrt_frame_assemble_device(self._h, C.byref(frame), C.c_void_p(d_compact_hits),
+                                                     C.c_void_p(d_compact_vis) if d_compact_vis else None,
+                                                     C.c_uint64(slots_per_rank), C.c_void_p(d_hits_out),
+                                                     C.c_void_p(d_vis_out) if d_vis_out else None, C.c_void_p(stream)))
 
     def launch_count(self) -> int:
         n = C.c_uint64(0)

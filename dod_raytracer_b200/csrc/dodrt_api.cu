@@ -428,6 +428,33 @@ int dodrt_trace_shadow_device(dodrt_scene *s, const dodrt_frame *frame, const fl
                        static_cast<cudaStream_t>(stream));
 }
 
+int dodrt_frame_assemble_device(dodrt_scene *s, const dodrt_frame *frame, const dodrt_hit *d_compact_hits,
+                                const uint8_t *d_compact_visible, uint64_t slots_per_rank, dodrt_hit *d_hits_out,
+                                uint8_t *d_visible_out, void *stream)
+{
+    if (!s) return fail(DODRT_E_INVALID, "scene is NULL");
+    int rc = checkFrame(frame);
+    if (rc != DODRT_OK) return rc;
+    if (!d_compact_hits || !d_hits_out) return fail(DODRT_E_INVALID, "NULL hit buffer");
+    if ((d_visible_out != nullptr) != (d_compact_visible != nullptr)) {
+        return fail(DODRT_E_INVALID, "visibility input and output must both be given or both be NULL");
+    }
+    dodrt_frame rank0 = *frame;
+    rank0.first_tile = 0;
+    if (slots_per_rank < frameSlots(&rank0)) {
+        return fail(DODRT_E_INVALID, "slots_per_rank %llu is smaller than rank 0's %llu slots",
+                    (unsigned long long)slots_per_rank, (unsigned long long)frameSlots(&rank0));
+    }
+    DeviceGuard guard(s->device);
+    if (!guard.ok) return fail(DODRT_E_CUDA, "cannot select device %d", s->device);
+    uint32_t tilesX, localTiles;
+    frameTiles(frame, &tilesX, &localTiles);
+    CUDA_TRY(launch_assemble(*frame, tilesX, d_compact_hits, d_compact_visible, slots_per_rank, d_hits_out,
+                             d_visible_out, static_cast<cudaStream_t>(stream)));
+    s->launches.fetch_add(1);
+    return DODRT_OK;
+}
+
 // ---- host-buffer entry points -------------------------------------------------------------------
 
 int dodrt_intersect(dodrt_scene *s, const dodrt_ray *rays, uint64_t num_rays, uint32_t classes, dodrt_hit *hits)

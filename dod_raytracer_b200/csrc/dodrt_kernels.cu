@@ -246,6 +246,29 @@ __global__ void repack_triangles_kernel(const float *__restrict__ lanes, uint32_
     tris[idx * 3 + 2] = make_float4(Cz - Az, 0.0f, 0.0f, 0.0f);
 }
 
+// Inverse of slot_to_pixel over all ranks: pixel -> (rank, slot).  Pure data movement (16+1 B per pixel).
+__global__ void assemble_kernel(const dodrt_frame f, uint32_t tilesX, const float4 *__restrict__ compactHits,
+                                const uint8_t *__restrict__ compactVis, uint64_t slotsPerRank,
+                                float4 *__restrict__ hitsOut, uint8_t *__restrict__ visOut)
+{
+    const uint64_t pixel = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (pixel >= (uint64_t)f.width * f.height) {
+        return;
+    }
+    const uint32_t col = (uint32_t)(pixel % f.width), row = (uint32_t)(pixel / f.width);
+    const uint32_t tx = col / f.tile_w, ty = row / f.tile_h;
+    const uint32_t tile = ty * tilesX + tx;
+    const uint32_t rank = tile % f.tile_stride, localTile = tile / f.tile_stride;
+    const uint32_t ix = col - tx * f.tile_w, iy = row - ty * f.tile_h;
+    const uint32_t block = (iy >> 2) * (f.tile_w >> 3) + (ix >> 3);
+    const uint32_t in = block * 32u + (iy & 3u) * 8u + (ix & 7u);
+    const uint64_t src = (uint64_t)rank * slotsPerRank + (uint64_t)localTile * f.tile_w * f.tile_h + in;
+    hitsOut[pixel] = compactHits[src];
+    if (visOut) {
+        visOut[pixel] = compactVis[src];
+    }
+}
+
 template <int MODE> cudaError_t config_for(int device, LaunchConfig *cfg)
 {
     int sms = 0, perSm = 0;
@@ -279,6 +302,18 @@ cudaError_t launch_trace(TraceMode mode, const TraceParams &p, const LaunchConfi
     case kModePrimary: trace_kernel<kModePrimary><<<cfg.grid, cfg.block, 0, stream>>>(p); break;
     default: trace_kernel<kModeShadow><<<cfg.grid, cfg.block, 0, stream>>>(p); break;
     }
+    return cudaGetLastError();
+}
+
+cudaError_t launch_assemble(const dodrt_frame &frame, uint32_t tiles_x, const dodrt_hit *compactHits,
+                            const uint8_t *compactVis, uint64_t slotsPerRank, dodrt_hit *hitsOut, uint8_t *visOut,
+                            cudaStream_t stream)
+{
+    const uint64_t n = (uint64_t)frame.width * frame.height;
+    const int block = 256;
+    assemble_kernel<<<(unsigned)((n + block - 1) / block), block, 0, stream>>>(
+        frame, tiles_x, reinterpret_cast<const float4 *>(compactHits), compactVis, slotsPerRank,
+        reinterpret_cast<float4 *>(hitsOut), visOut);
     return cudaGetLastError();
 }
 

@@ -38,6 +38,11 @@ struct LaunchConfig {
 cudaError_t trace_launch_config(int device, TraceMode mode, LaunchConfig *cfg);
 cudaError_t launch_trace(TraceMode mode, const TraceParams &p, const LaunchConfig &cfg, cudaStream_t stream);
 
+// Multi-GPU: gathered per-rank compact results -> row-major frame (one thread per pixel).
+cudaError_t launch_assemble(const dodrt_frame &frame, uint32_t tiles_x, const dodrt_hit *compactHits,
+                            const uint8_t *compactVis, uint64_t slotsPerRank, dodrt_hit *hitsOut, uint8_t *visOut,
+                            cudaStream_t stream);
+
 // Upload helper: reference lanes (288 B, SoA of 8) -> per-triangle 48-B records with AB/AC.
 cudaError_t launch_repack_triangles(const float *d_lanes, uint32_t num_lanes, float4 *d_tris, cudaStream_t stream);
 

@@ -172,6 +172,14 @@ DODRT_API int dodrt_trace_primary_device(dodrt_scene *scene, const dodrt_frame *
 DODRT_API int dodrt_trace_shadow_device(dodrt_scene *scene, const dodrt_frame *frame, const float *d_xs, const float *d_ys,
                               const dodrt_hit *d_hits, const float light[3], uint8_t *d_visible, void *stream);
 
+/* Multi-GPU frame assembly.  After an image-tile split over N ranks (frame->tile_stride = N, rank r traced
+ * with first_tile = r, compact = 1) and a gather that places rank r's compact results at
+ * d_compact_*[r * slots_per_rank ...], this writes the row-major full frame: hits_out[row*width+col] and,
+ * when both visibility pointers are non-NULL, visible_out[row*width+col].  frame->first_tile is ignored. */
+DODRT_API int dodrt_frame_assemble_device(dodrt_scene *scene, const dodrt_frame *frame, const dodrt_hit *d_compact_hits,
+                                          const uint8_t *d_compact_visible, uint64_t slots_per_rank,
+                                          dodrt_hit *d_hits_out, uint8_t *d_visible_out, void *stream);
+
 /* ---- frame helpers (host only, no GPU work) -------------------------------------------------- */
 /* number of result slots a call with this frame description writes when compact = 1 */
 DODRT_API int dodrt_frame_local_pixels(const dodrt_frame *frame, uint64_t *slots);

@@ -484,6 +484,54 @@ void ref_render_bands(uint8_t *image, int nthreads)
     for (auto &t : threads) t.join();
 }
 
+// One frame the way the reference's rayTrace does it (main.cpp:297-334) reduced to bounce k = 0 and one
+// light: per pixel the closest-hit chain, then canSeeLight's any-hit chain from the hit point.  Rows are
+// split into contiguous bands over threads exactly like main.cpp:371-393.  This is the CPU baseline the
+// benchmark times; ids are not recovered here (real attributes stay in place).
+void ref_trace_frame(uint32_t classes, const float light[3], float *tOut, uint8_t *visible, int nthreads)
+{
+    setProbe(false);
+    const unsigned W = Config::Width, H = Config::Height;
+    std::vector<float> xs(W), ys(H);
+    {
+        glm::vec3 rayDir = {-Config::Ratio, 1.0f, 1};
+        float widthStep = 2.0f * Config::Ratio / Config::Width;
+        float heightStep = 2.0f / Config::Height;
+        for (unsigned j = 0; j < W; j++) { xs[j] = rayDir.x; rayDir.x += widthStep; }
+        for (unsigned i = 0; i < H; i++) { ys[i] = rayDir.y; rayDir.y -= heightStep; }
+    }
+    const glm::vec3 lightPos(light[0], light[1], light[2]);
+    parallelFor(H, nthreads, [&](uint64_t rowLo, uint64_t rowHi) {
+        for (uint64_t i = rowLo; i < rowHi; i++) {
+            for (unsigned j = 0; j < W; j++) {
+                HitRecord hr;
+                hr.t = std::numeric_limits<float>::infinity();
+                _Intersect in{.rayDir = glm::normalize(glm::vec3(xs[j], ys[i], 1.0f)),
+                              .rayOrigin = {0, 0, -4.9},
+                              .record = hr};
+                bool hit = runChain(in, classes);
+                const uint64_t k = i * W + j;
+                tOut[k] = hit ? hr.t : std::numeric_limits<float>::infinity();
+                uint8_t vis = 0;
+                if (hit) {
+                    glm::vec3 lightDir = lightPos - hr.hitPoint;
+                    float lightDistance = glm::length(lightDir);
+                    lightDir /= lightDistance;
+                    HitRecord shr;
+                    shr.t = lightDistance;
+                    _Intersect sin{.rayDir = lightDir,
+                                   .rayOrigin = hr.hitPoint + lightDir * 0.01f,
+                                   .returnOnAny = true,
+                                   .clippingDistance = lightDistance,
+                                   .record = shr};
+                    vis = runChain(sin, classes) ? 0 : 1;
+                }
+                visible[k] = vis;
+            }
+        }
+    });
+}
+
 int ref_hardware_threads() { return static_cast<int>(std::thread::hardware_concurrency()); }
 
 } // extern "C"

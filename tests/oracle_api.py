@@ -260,6 +260,15 @@ class RefLib:
                                        C.c_int(nthreads))
         return recs
 
+    def trace_frame(self, width, height, classes, light, nthreads=1):
+        """reference per-pixel loop at bounce 0 with one light (ref_trace_frame): (t [n], visible [n])"""
+        self.set_config(width, height)
+        light = np.ascontiguousarray(light, np.float32)
+        t = np.zeros(width * height, np.float32)
+        vis = np.zeros(width * height, np.uint8)
+        self.lib.ref_trace_frame(C.c_uint32(classes), _ptr(light), _ptr(t), _ptr(vis), C.c_int(nthreads))
+        return t, vis
+
     def render(self, width, height, nthreads=0):
         self.set_config(width, height)
         img = np.zeros((height, width, 3), np.uint8)
