@@ -32,6 +32,7 @@ EXPORTED_SYMBOLS = [
     "dodrt_abi_version", "dodrt_last_error", "dodrt_device_count",
     "dodrt_scene_create", "dodrt_scene_destroy", "dodrt_scene_set_kdtree", "dodrt_scene_set_spheres",
     "dodrt_scene_set_planes", "dodrt_scene_set_cylinders", "dodrt_scene_set_boxes", "dodrt_scene_set_epsilon",
+    "dodrt_scene_set_kernel_variant",
     "dodrt_intersect", "dodrt_trace_primary", "dodrt_trace_shadow", "dodrt_trace_frame",
     "dodrt_intersect_device", "dodrt_trace_primary_device", "dodrt_trace_shadow_device",
     "dodrt_frame_assemble_device", "dodrt_frame_local_pixels", "dodrt_frame_pixel_map", "dodrt_scene_launch_count",
@@ -175,6 +176,9 @@ class Scene:
     def set_cylinders(self, cylinders: np.ndarray):
         cyl = np.ascontiguousarray(cylinders, CYL_DT)
         _check(self._lib.dodrt_scene_set_cylinders(self._h, _ptr(cyl), C.c_uint32(len(cyl))))
+
+    def set_kernel_variant(self, variant: int):
+        _check(self._lib.dodrt_scene_set_kernel_variant(self._h, C.c_int(variant)))
 
     def set_epsilon(self, eps: float):
         _check(self._lib.dodrt_scene_set_epsilon(self._h, C.c_float(eps)))

@@ -83,10 +83,14 @@ struct dodrt_scene {
     unsigned long long *d_counters = nullptr;
     std::atomic<uint32_t> nextCounter{0};
     std::atomic<uint64_t> launches{0};
-    LaunchConfig cfg[3]{};
+    LaunchConfig cfg[kNumVariants][3]{};
+    int variant = kDefaultVariant;
     uint32_t treeDepth = 0;
     std::mutex mutex; // guards scene mutation and the lazily created staging stream
     cudaStream_t stream = nullptr;
+    // staging memory of the host-buffer entry points: a private pool that keeps freed blocks cached
+    // (release threshold = max), so a per-frame call does not pay for physical allocation every time
+    cudaMemPool_t pool = nullptr;
 };
 
 namespace {
@@ -172,6 +176,16 @@ int ensureStream(dodrt_scene *s)
     if (!s->stream) {
         CUDA_TRY(cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking));
     }
+    if (!s->pool) {
+        cudaMemPoolProps props{};
+        props.allocType = cudaMemAllocationTypePinned;
+        props.handleTypes = cudaMemHandleTypeNone;
+        props.location.type = cudaMemLocationTypeDevice;
+        props.location.id = s->device;
+        CUDA_TRY(cudaMemPoolCreate(&s->pool, &props));
+        uint64_t keep = UINT64_MAX;
+        CUDA_TRY(cudaMemPoolSetAttribute(s->pool, cudaMemPoolAttrReleaseThreshold, &keep));
+    }
     return DODRT_OK;
 }
 
@@ -195,10 +209,11 @@ int launchFrame(dodrt_scene *s, TraceMode mode, const dodrt_frame *frame, const 
         p.light[2] = light[2];
     }
     p.counter = nextCounter(s);
+    p.variant = s->variant;
     if (p.count == 0) {
         return DODRT_OK;
     }
-    CUDA_TRY(launch_trace(mode, p, s->cfg[mode], stream));
+    CUDA_TRY(launch_trace(mode, p, s->cfg[p.variant][mode], stream));
     s->launches.fetch_add(1);
     return DODRT_OK;
 }
@@ -233,8 +248,11 @@ int dodrt_scene_create(int device, dodrt_scene **scene)
     s->device = device;
     s->dev.epsilon = 0.0001f; // Config::Epsilon default, config.h:9
     cudaError_t e = cudaMalloc(&s->d_counters, sizeof(unsigned long long) * kCounterSlots);
-    for (int m = 0; m < 3 && e == cudaSuccess; m++) {
-        e = trace_launch_config(device, (TraceMode)m, &s->cfg[m]);
+    s->variant = default_variant();
+    for (int v = 0; v < kNumVariants; v++) {
+        for (int m = 0; m < 3 && e == cudaSuccess; m++) {
+            e = trace_launch_config(device, (TraceMode)m, v, &s->cfg[v][m]);
+        }
     }
     if (e != cudaSuccess) {
         cudaFree(s->d_counters);
@@ -251,6 +269,7 @@ int dodrt_scene_destroy(dodrt_scene *s)
     DeviceGuard guard(s->device);
     cudaDeviceSynchronize();
     if (s->stream) cudaStreamDestroy(s->stream);
+    if (s->pool) cudaMemPoolDestroy(s->pool);
     freeDevice(s->d_nodes);
     freeDevice(s->d_tris);
     freeDevice(s->d_spheres);
@@ -373,6 +392,15 @@ int dodrt_scene_set_cylinders(dodrt_scene *s, const dodrt_cylinder *cylinders, u
     return DODRT_OK;
 }
 
+int dodrt_scene_set_kernel_variant(dodrt_scene *s, int variant)
+{
+    if (!s) return fail(DODRT_E_INVALID, "scene is NULL");
+    if (variant >= kNumVariants) return fail(DODRT_E_INVALID, "kernel variant %d out of range [0,%d)", variant, kNumVariants);
+    std::lock_guard<std::mutex> lock(s->mutex);
+    s->variant = variant < 0 ? default_variant() : variant;
+    return DODRT_OK;
+}
+
 int dodrt_scene_set_epsilon(dodrt_scene *s, float epsilon)
 {
     if (!s) return fail(DODRT_E_INVALID, "scene is NULL");
@@ -398,7 +426,8 @@ int dodrt_intersect_device(dodrt_scene *s, const dodrt_ray *d_rays, uint64_t num
     p.count = num_rays;
     p.hits = d_hits;
     p.counter = nextCounter(s);
-    CUDA_TRY(launch_trace(kModeRays, p, s->cfg[kModeRays], static_cast<cudaStream_t>(stream)));
+    p.variant = s->variant;
+    CUDA_TRY(launch_trace(kModeRays, p, s->cfg[p.variant][kModeRays], static_cast<cudaStream_t>(stream)));
     s->launches.fetch_add(1);
     return DODRT_OK;
 }
@@ -469,8 +498,8 @@ int dodrt_intersect(dodrt_scene *s, const dodrt_ray *rays, uint64_t num_rays, ui
     dodrt_ray *d_rays = nullptr;
     dodrt_hit *d_hits = nullptr;
     cudaStream_t st = s->stream;
-    CUDA_TRY(cudaMallocAsync(&d_rays, num_rays * sizeof(dodrt_ray), st));
-    cudaError_t e = cudaMallocAsync(&d_hits, num_rays * sizeof(dodrt_hit), st);
+    CUDA_TRY(cudaMallocFromPoolAsync(&d_rays, num_rays * sizeof(dodrt_ray), s->pool, st));
+    cudaError_t e = cudaMallocFromPoolAsync(&d_hits, num_rays * sizeof(dodrt_hit), s->pool, st);
     if (e == cudaSuccess) e = cudaMemcpyAsync(d_rays, rays, num_rays * sizeof(dodrt_ray), cudaMemcpyHostToDevice, st);
     if (e == cudaSuccess) {
         rc = dodrt_intersect_device(s, d_rays, num_rays, classes, d_hits, st);
@@ -506,9 +535,9 @@ int dodrt_trace_frame(dodrt_scene *s, const dodrt_frame *frame, const float *xs,
     dodrt_hit *d_hits = nullptr;
     uint8_t *d_vis = nullptr;
     const size_t tableFloats = (size_t)frame->width + frame->height;
-    CUDA_TRY(cudaMallocAsync(&d_tables, tableFloats * sizeof(float), st));
-    cudaError_t e = cudaMallocAsync(&d_hits, slots * sizeof(dodrt_hit), st);
-    if (e == cudaSuccess && num_lights) e = cudaMallocAsync(&d_vis, slots * (size_t)num_lights, st);
+    CUDA_TRY(cudaMallocFromPoolAsync(&d_tables, tableFloats * sizeof(float), s->pool, st));
+    cudaError_t e = cudaMallocFromPoolAsync(&d_hits, slots * sizeof(dodrt_hit), s->pool, st);
+    if (e == cudaSuccess && num_lights) e = cudaMallocFromPoolAsync(&d_vis, slots * (size_t)num_lights, s->pool, st);
     if (e == cudaSuccess) e = cudaMemcpyAsync(d_tables, xs, frame->width * sizeof(float), cudaMemcpyHostToDevice, st);
     if (e == cudaSuccess) {
         e = cudaMemcpyAsync(d_tables + frame->width, ys, frame->height * sizeof(float), cudaMemcpyHostToDevice, st);
@@ -563,9 +592,9 @@ int dodrt_trace_shadow(dodrt_scene *s, const dodrt_frame *frame, const float *xs
     float *d_tables = nullptr;
     dodrt_hit *d_hits = nullptr;
     uint8_t *d_vis = nullptr;
-    CUDA_TRY(cudaMallocAsync(&d_tables, ((size_t)frame->width + frame->height) * sizeof(float), st));
-    cudaError_t e = cudaMallocAsync(&d_hits, slots * sizeof(dodrt_hit), st);
-    if (e == cudaSuccess) e = cudaMallocAsync(&d_vis, slots, st);
+    CUDA_TRY(cudaMallocFromPoolAsync(&d_tables, ((size_t)frame->width + frame->height) * sizeof(float), s->pool, st));
+    cudaError_t e = cudaMallocFromPoolAsync(&d_hits, slots * sizeof(dodrt_hit), s->pool, st);
+    if (e == cudaSuccess) e = cudaMallocFromPoolAsync(&d_vis, slots, s->pool, st);
     if (e == cudaSuccess) e = cudaMemcpyAsync(d_tables, xs, frame->width * sizeof(float), cudaMemcpyHostToDevice, st);
     if (e == cudaSuccess) {
         e = cudaMemcpyAsync(d_tables + frame->width, ys, frame->height * sizeof(float), cudaMemcpyHostToDevice, st);

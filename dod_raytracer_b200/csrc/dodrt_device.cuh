@@ -121,6 +121,71 @@ __device__ __forceinline__ bool triangle_test(const float4 q0, const float4 q1, 
     return true;
 }
 
+// Same result as triangle_test, bit for bit, but the IEEE division (a ~12-instruction sequence) and the
+// products that follow it are only executed for triangles that survive CONSERVATIVE sign / magnitude
+// tests on the un-divided numerators.  With a = dot(T,p), b = dot(D,q), c = dot(AC,q):
+//   u = fl(a * fl(1/det)) > 0  requires a != 0 and sign(a) == sign(det)       (fl(1/det) has det's sign)
+//   u < 1                      fails for sure when |a| > 1.00001 |det|        (two roundings ~ 2^-23 << 1e-5)
+//   v > 0, (u+v) < 1, t > 0    likewise with b, |a|+|b|, c
+// A triangle is only rejected early when the reference's own compare is guaranteed to reject it; all
+// survivors (a few %) run the reference's exact expression sequence, so accepted (t,u,v) are identical.
+// NaN/inf/denormal inputs simply fall through to the exact path.
+__device__ __forceinline__ bool sign_differs_or_zero(float x, float det)
+{
+    return (int)(__float_as_uint(x) ^ __float_as_uint(det)) < 0 || x == 0.0f;
+}
+
+__device__ __forceinline__ bool triangle_test_fast(const float4 q0, const float4 q1, const float4 q2, const float o[3],
+                                                   const float d[3], float maxDist, float &tOut, float &uOut,
+                                                   float &vOut)
+{
+    const float Ax = q0.x, Ay = q0.y, Az = q0.z;
+    const float ABx = q0.w, ABy = q1.x, ABz = q1.y;
+    const float ACx = q1.z, ACy = q1.w, ACz = q2.x;
+    float px = d[1] * ACz - d[2] * ACy;
+    float py = d[2] * ACx - d[0] * ACz;
+    float pz = d[0] * ACy - d[1] * ACx;
+    float det = dot3(px, py, pz, ABx, ABy, ABz);
+    if (!(fabsf(det) > 0.0f)) {
+        return false;
+    }
+    float tx = o[0] - Ax, ty = o[1] - Ay, tz = o[2] - Az;
+    float a = dot3(tx, ty, tz, px, py, pz);
+    const float lim = fabsf(det) * 1.00001f;
+    if (sign_differs_or_zero(a, det) || fabsf(a) > lim) {
+        return false;
+    }
+    float qx = ty * ABz - tz * ABy;
+    float qy = tz * ABx - tx * ABz;
+    float qz = tx * ABy - ty * ABx;
+    float b = dot3(d[0], d[1], d[2], qx, qy, qz);
+    if (sign_differs_or_zero(b, det) || fabsf(a) + fabsf(b) > lim) {
+        return false;
+    }
+    float c = dot3(ACx, ACy, ACz, qx, qy, qz);
+    if (sign_differs_or_zero(c, det)) {
+        return false;
+    }
+    // exact tail: triangle.cpp:81-111 in the reference's order
+    float inv_det = 1.0f / det;
+    float u = a * inv_det;
+    if (!(u > 0.0f && u < 1.0f)) {
+        return false;
+    }
+    float v = b * inv_det;
+    if (!(v > 0.0f && (u + v) < 1.0f)) {
+        return false;
+    }
+    float t = c * inv_det;
+    if (!(t > 0.0f && t < maxDist)) {
+        return false;
+    }
+    tOut = t;
+    uOut = u;
+    vOut = v;
+    return true;
+}
+
 // Sphere::intersect_impl, sphere.cpp:26-160 (lane-structured for the any-hit break, sphere.cpp:138-141)
 __device__ __forceinline__ bool sphere_query(const DeviceScene &s, const float o[3], const float d[3], bool any,
                                              float clip, Hit &hit)

@@ -3,28 +3,47 @@
 // Compile with: nvcc -gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -fmad=false
 // (-fmad=false is part of the numerical contract, see dodrt_device.cuh).
 //
-// Kernel shape (v1): persistent warps.  Each warp claims 32 consecutive work items at a time from a
-// global counter (one atomic per warp per claim), every thread runs ONE ray through the reference's
-// query chain Sphere -> [Box] -> Plane -> Cylinder -> KDTree with a per-thread short stack, and the
-// warp claims again when all of its rays are done.  In the frame modes 32 consecutive work items
-// are an 8x4 pixel block, so a warp's rays are coherent and its node / triangle fetches coalesce
-// into broadcasts.  The tensor cores are idle by design: the path has no dense contraction.
+// All kernels are persistent: a warp claims 32 consecutive work items at a time from a global
+// counter (one atomic per claim); in the frame modes 32 consecutive items are an 8x4 pixel block, so a
+// warp's rays are coherent.  Every thread owns ONE ray, runs the analytic classes of the reference's
+// query chain (Sphere -> [Box] -> Plane -> Cylinder) and then the kd-tree with a per-thread short stack.
+// The tensor cores are idle by design: the path has no dense contraction.
+//
+// Kernel variants (TraceParams::variant, env DODRT_VARIANT, default = kDefaultVariant):
+//   0  per-thread traversal loop, exact reference-order triangle test                (round-1 baseline)
+//   1  same loop, division-deferring triangle test (triangle_test_fast)
+//   2  warp-voted traversal: the warp alternates between "one kd node step" and "one triangle lane
+//      (8 triangles)" and always runs the phase the MAJORITY of its live rays is waiting for, so at
+//      least half of the live lanes do useful work in every instruction (profiles/r01_*: the baseline
+//      loop ran with 11.8 of 32 lanes active because rays at interior nodes waited for whole leaves).
+// Every variant computes identical results (parity tests run all of them).
 #include "dodrt_kernels.cuh"
+
+#include <cstdlib>
 
 namespace dodrt {
 
 namespace {
+
+constexpr float kInfinity = __builtin_huge_valf();
 
 __device__ __forceinline__ float pick(const float v[3], uint32_t axis)
 {
     return axis == 0 ? v[0] : (axis == 1 ? v[1] : v[2]);
 }
 
-// KDTree::intersect, kdtree.cpp:263-361, with Triangle::intersectInRange (triangle.cpp:22-177)
-// inlined for the leaves.  `clip` is _Intersect::clippingDistance (in/out, kdtree.cpp:343).
-template <bool ANY>
-__device__ __forceinline__ bool kdtree_query(const DeviceScene &s, const float o[3], const float d[3], float &clip,
-                                             Hit &hit)
+template <bool FAST>
+__device__ __forceinline__ bool tri_test(const float4 *__restrict__ tri, const float o[3], const float d[3], float maxDist,
+                                         float &t, float &u, float &v)
+{
+    const float4 q0 = __ldg(tri), q1 = __ldg(tri + 1), q2 = __ldg(tri + 2);
+    return FAST ? triangle_test_fast(q0, q1, q2, o, d, maxDist, t, u, v) : triangle_test(q0, q1, q2, o, d, maxDist, t, u, v);
+}
+
+// ---- variants 0/1: KDTree::intersect, kdtree.cpp:263-361, as one loop per thread -----------------------------
+template <bool FAST>
+__device__ __forceinline__ bool kdtree_query(const DeviceScene &s, const float o[3], const float d[3], bool any,
+                                             float &clip, Hit &hit)
 {
     if (s.num_nodes == 0) {
         return false;
@@ -71,16 +90,15 @@ __device__ __forceinline__ bool kdtree_query(const DeviceScene &s, const float o
             const uint32_t firstTri = n.y * kLane;
             const float4 *tri = s.tris + (size_t)firstTri * 3;
             for (uint32_t k = 0; k < numTris; k++, tri += 3) {
-                const float4 q0 = __ldg(tri), q1 = __ldg(tri + 1), q2 = __ldg(tri + 2);
                 float t, u, v;
-                if (triangle_test(q0, q1, q2, o, d, clip, t, u, v)) {
+                if (tri_test<FAST>(tri, o, d, clip, t, u, v)) {
                     clip = t; // running maximumDistance, then kdtree.cpp:343
                     hit.t = t;
                     hit.prim = (DODRT_KIND_TRIANGLE << DODRT_KIND_SHIFT) | (firstTri + k);
                     hit.u = u;
                     hit.v = v;
                     found = true;
-                    if (ANY) { // kdtree.cpp:338-341: only the boolean is defined for any-hit
+                    if (any) { // kdtree.cpp:338-341: only the boolean is defined for any-hit
                         return true;
                     }
                 }
@@ -98,41 +116,180 @@ __device__ __forceinline__ bool kdtree_query(const DeviceScene &s, const float o
     return found;
 }
 
-// The query chain: closest hit main.cpp:312-321, any hit main.cpp:198-217.
-template <bool ANY>
-__device__ __forceinline__ bool query_chain(const DeviceScene &s, uint32_t classes, const float o[3], const float d[3],
-                                            float clip, Hit &hit)
+// ---- variant 2: the same traversal as a warp-voted state machine ---------------------------------------------
+// Per-thread state: `live` (ray still traversing), a pending triangle range [triCur, triEnd) of the leaf
+// it is in, the node to visit next, the parametric interval, and the stack.  The reference's order of
+// events per ray is untouched (nodes front to back, triangles of a leaf in id order, strict `<`), only
+// the interleaving ACROSS the rays of a warp changes.
+struct TreeState {
+    float inv[3];
+    float tmin, tmax;
+    uint32_t node;
+    uint32_t triCur, triEnd;
+    int sp;
+    bool live;
+};
+
+__device__ __forceinline__ void tree_pop(TreeState &st, const uint32_t *stackNode, const float *stackTmin,
+                                         const float *stackTmax)
 {
+    if (st.sp > 0) { // kdtree.cpp:347-357
+        --st.sp;
+        st.node = stackNode[st.sp];
+        st.tmin = stackTmin[st.sp];
+        st.tmax = stackTmax[st.sp];
+    } else {
+        st.live = false;
+    }
+}
+
+template <bool FAST>
+__device__ __forceinline__ bool kdtree_query_voted(const DeviceScene &s, bool enter, const float o[3], const float d[3],
+                                                   bool any, float &clip, Hit &hit)
+{
+    TreeState st;
+    st.live = false;
+    st.triCur = st.triEnd = 0;
+    st.sp = 0;
+    st.node = 0;
+    st.tmin = st.tmax = 0.0f;
+    st.inv[0] = st.inv[1] = st.inv[2] = 0.0f;
+    if (enter && s.num_nodes != 0) {
+        st.inv[0] = 1.0f / d[0]; // kdtree.cpp:271
+        st.inv[1] = 1.0f / d[1];
+        st.inv[2] = 1.0f / d[2];
+        st.live = slab(s.bmin, s.bmax, o, st.inv, clip, st.tmin, st.tmax) && !(st.tmin > clip); // kdtree.cpp:274
+    }
+    uint32_t stackNode[kMaxStack];
+    float stackTmin[kMaxStack];
+    float stackTmax[kMaxStack];
     bool found = false;
+    for (;;) {
+        const bool wantLeaf = st.live && st.triCur < st.triEnd;
+        const bool wantNode = st.live && !wantLeaf;
+        const unsigned leafMask = __ballot_sync(0xffffffffu, wantLeaf);
+        const unsigned nodeMask = __ballot_sync(0xffffffffu, wantNode);
+        if ((leafMask | nodeMask) == 0u) {
+            break;
+        }
+        if (__popc(leafMask) >= __popc(nodeMask)) {
+            if (wantLeaf) { // one reference lane = 8 consecutive triangle slots (triangle.cpp:43-140)
+                const float4 *tri = s.tris + (size_t)st.triCur * 3;
+#pragma unroll 4
+                for (uint32_t k = 0; k < (uint32_t)kLane; k++, tri += 3) {
+                    float t, u, v;
+                    if (tri_test<FAST>(tri, o, d, clip, t, u, v)) {
+                        clip = t;
+                        hit.t = t;
+                        hit.prim = (DODRT_KIND_TRIANGLE << DODRT_KIND_SHIFT) | (st.triCur + k);
+                        hit.u = u;
+                        hit.v = v;
+                        found = true;
+                    }
+                }
+                st.triCur += kLane;
+                if (any && found) {
+                    st.live = false; // kdtree.cpp:338-341
+                } else if (st.triCur == st.triEnd) {
+                    tree_pop(st, stackNode, stackTmin, stackTmax);
+                }
+            }
+        } else if (wantNode) {
+            if (clip < st.tmin) { // kdtree.cpp:286-289
+                st.live = false;
+            } else {
+                const uint2 n = __ldg(&s.nodes[st.node]);
+                if ((n.x & 3u) != kLeafFlag) {
+                    const uint32_t axis = n.x & 3u;
+                    const float split = __uint_as_float(n.y);
+                    const float oa = pick(o, axis);
+                    const float tPlane = (split - oa) * pick(st.inv, axis);
+                    const bool leftFirst = (oa < split) || (oa == split && pick(d, axis) <= 0.0f);
+                    const uint32_t below = st.node + 1, above = n.x >> 2;
+                    const uint32_t nearChild = leftFirst ? below : above;
+                    const uint32_t farChild = leftFirst ? above : below;
+                    if (tPlane > st.tmax || tPlane <= 0.0f) {
+                        st.node = nearChild;
+                    } else if (tPlane < st.tmin) {
+                        st.node = farChild;
+                    } else {
+                        stackNode[st.sp] = farChild;
+                        stackTmin[st.sp] = tPlane;
+                        stackTmax[st.sp] = st.tmax;
+                        ++st.sp;
+                        st.node = nearChild;
+                        st.tmax = tPlane;
+                    }
+                } else {
+                    const uint32_t numTris = (n.x >> 2) * kLane;
+                    if (numTris == 0) {
+                        tree_pop(st, stackNode, stackTmin, stackTmax);
+                    } else {
+                        st.triCur = n.y * kLane;
+                        st.triEnd = st.triCur + numTris;
+                    }
+                }
+            }
+        }
+    }
+    return found;
+}
+
+// The analytic part of the query chain: closest hit main.cpp:312-319, any hit main.cpp:198-208.
+// Returns true when the any-hit query is already decided.
+__device__ __forceinline__ bool analytic_chain(const DeviceScene &s, uint32_t classes, const float o[3],
+                                               const float d[3], bool any, float &clip, Hit &hit, bool &found)
+{
     Hit h;
-    hit.t = clip;
-    hit.prim = DODRT_MISS;
-    hit.u = hit.v = 0.0f;
-    if ((classes & DODRT_CLS_SPHERE) && s.num_spheres && sphere_query(s, o, d, ANY, clip, h)) {
+    if ((classes & DODRT_CLS_SPHERE) && s.num_spheres && sphere_query(s, o, d, any, clip, h)) {
         hit = h;
         found = true;
-        if (ANY) return true;
+        if (any) return true;
         clip = h.t;
     }
-    if ((classes & DODRT_CLS_BOX) && s.num_boxes && box_query(s, o, d, ANY, clip, h)) {
+    if ((classes & DODRT_CLS_BOX) && s.num_boxes && box_query(s, o, d, any, clip, h)) {
         hit = h;
         found = true;
-        if (ANY) return true;
+        if (any) return true;
         clip = h.t;
     }
     if ((classes & DODRT_CLS_PLANE) && s.num_planes && plane_query(s, o, d, clip, h)) {
         hit = h;
         found = true;
-        if (ANY) return true;
+        if (any) return true;
         clip = h.t;
     }
     if ((classes & DODRT_CLS_CYLINDER) && s.num_cylinders && cylinder_query(s, o, d, clip, h)) {
         hit = h;
         found = true;
-        if (ANY) return true;
+        if (any) return true;
         clip = h.t;
     }
-    if ((classes & DODRT_CLS_TREE) && kdtree_query<ANY>(s, o, d, clip, h)) {
+    return false;
+}
+
+// One full query for this thread's ray.  `valid` = the thread has a ray at all; in the voted variant every
+// lane of the warp must call this (the traversal is warp-synchronous).
+template <int VARIANT>
+__device__ __forceinline__ bool query(const DeviceScene &s, uint32_t classes, bool valid, const float o[3],
+                                      const float d[3], bool any, float clip, Hit &hit)
+{
+    bool found = false;
+    hit.t = clip;
+    hit.prim = DODRT_MISS;
+    hit.u = hit.v = 0.0f;
+    bool decided = !valid;
+    if (valid) {
+        decided = analytic_chain(s, classes, o, d, any, clip, hit, found);
+    }
+    const bool enter = !decided && (classes & DODRT_CLS_TREE);
+    Hit h;
+    if (VARIANT == 2) {
+        if (kdtree_query_voted<true>(s, enter, o, d, any, clip, h)) {
+            hit = h;
+            found = true;
+        }
+    } else if (enter && kdtree_query<VARIANT == 1>(s, o, d, any, clip, h)) {
         hit = h;
         found = true;
     }
@@ -157,7 +314,7 @@ __device__ __forceinline__ bool slot_to_pixel(const dodrt_frame &f, uint32_t til
     return col < f.width && row < f.height;
 }
 
-template <int MODE> __global__ void __launch_bounds__(128) trace_kernel(const TraceParams p)
+template <int MODE, int VARIANT> __global__ void __launch_bounds__(128) trace_kernel(const TraceParams p)
 {
     const uint32_t lane = threadIdx.x & 31u;
     for (;;) {
@@ -170,59 +327,60 @@ template <int MODE> __global__ void __launch_bounds__(128) trace_kernel(const Tr
             break;
         }
         const uint64_t item = base + lane;
-        if (item >= p.count) {
-            continue;
-        }
+        const bool inRange = item < p.count;
         if (MODE == kModeRays) {
-            const float4 *src = reinterpret_cast<const float4 *>(p.rays + item);
-            const float4 a = __ldg(src), b = __ldg(src + 1);
-            const float o[3] = {a.x, a.y, a.z};
-            const float d[3] = {a.w, b.x, b.y};
-            const float clip = b.z;
-            const uint32_t flags = __float_as_uint(b.w);
+            float o[3] = {0.0f, 0.0f, 0.0f}, d[3] = {0.0f, 0.0f, 1.0f};
+            float clip = 0.0f;
+            bool any = false;
+            if (inRange) {
+                const float4 *src = reinterpret_cast<const float4 *>(p.rays + item);
+                const float4 a = __ldg(src), b = __ldg(src + 1);
+                o[0] = a.x, o[1] = a.y, o[2] = a.z;
+                d[0] = a.w, d[1] = b.x, d[2] = b.y;
+                clip = b.z;
+                any = (__float_as_uint(b.w) & DODRT_RAY_ANY) != 0u;
+            }
             Hit h;
-            bool found;
-            if (flags & DODRT_RAY_ANY) {
-                found = query_chain<true>(p.scene, p.classes, o, d, clip, h);
-                h.t = clip; // any-hit defines only hit/miss
-                h.prim = found ? 0u : DODRT_MISS;
-                h.u = h.v = 0.0f;
-            } else {
-                found = query_chain<false>(p.scene, p.classes, o, d, clip, h);
-            }
-            reinterpret_cast<float4 *>(p.hits)[item] = make_float4(h.t, __uint_as_float(h.prim), h.u, h.v);
-        } else {
-            uint32_t col, row;
-            const bool inside = slot_to_pixel(p.frame, p.tiles_x, item, col, row);
-            const uint64_t out = p.frame.compact ? item : (uint64_t)row * p.frame.width + col;
-            if (!inside) {
-                if (p.frame.compact) {
-                    if (MODE == kModePrimary) {
-                        reinterpret_cast<float4 *>(p.hits)[out] =
-                            make_float4(__int_as_float(0x7f800000), __uint_as_float(DODRT_MISS), 0.0f, 0.0f);
-                    } else {
-                        p.visible[out] = 0;
-                    }
+            const bool found = query<VARIANT>(p.scene, p.classes, inRange, o, d, any, clip, h);
+            if (inRange) {
+                if (any) { // any-hit defines only hit/miss
+                    h.t = clip;
+                    h.prim = found ? 0u : DODRT_MISS;
+                    h.u = h.v = 0.0f;
                 }
-                continue;
+                reinterpret_cast<float4 *>(p.hits)[item] = make_float4(h.t, __uint_as_float(h.prim), h.u, h.v);
             }
+        } else {
+            uint32_t col = 0, row = 0;
+            const bool inside = inRange && slot_to_pixel(p.frame, p.tiles_x, item, col, row);
+            const uint64_t out = p.frame.compact ? item : (uint64_t)row * p.frame.width + col;
             const float o[3] = {p.frame.origin[0], p.frame.origin[1], p.frame.origin[2]};
-            float d[3];
-            primary_dir(__ldg(p.xs + col), __ldg(p.ys + row), d);
+            float d[3] = {0.0f, 0.0f, 1.0f};
+            if (inside) {
+                primary_dir(__ldg(p.xs + col), __ldg(p.ys + row), d);
+            }
             if (MODE == kModePrimary) {
                 Hit h;
-                query_chain<false>(p.scene, p.classes, o, d, __int_as_float(0x7f800000), h);
-                reinterpret_cast<float4 *>(p.hits)[out] = make_float4(h.t, __uint_as_float(h.prim), h.u, h.v);
-            } else {
-                const float4 ph = reinterpret_cast<const float4 *>(p.hits)[out];
-                uint8_t vis = 0;
-                if (__float_as_uint(ph.y) != DODRT_MISS) {
-                    float so[3], sd[3], sclip;
-                    shadow_ray(o, d, ph.x, p.light, so, sd, sclip);
-                    Hit h;
-                    vis = query_chain<true>(p.scene, p.classes, so, sd, sclip, h) ? 0 : 1;
+                query<VARIANT>(p.scene, p.classes, inside, o, d, false, kInfinity, h);
+                if (inside || (inRange && p.frame.compact)) { // padded slots of edge tiles read as "miss"
+                    reinterpret_cast<float4 *>(p.hits)[out] = make_float4(h.t, __uint_as_float(h.prim), h.u, h.v);
                 }
-                p.visible[out] = vis;
+            } else {
+                bool shadowed = true, cast = false;
+                float so[3] = {0.0f, 0.0f, 0.0f}, sd[3] = {0.0f, 0.0f, 1.0f}, sclip = 0.0f;
+                if (inside) {
+                    const float4 ph = reinterpret_cast<const float4 *>(p.hits)[out];
+                    if (__float_as_uint(ph.y) != DODRT_MISS) {
+                        shadow_ray(o, d, ph.x, p.light, so, sd, sclip);
+                        cast = true;
+                    }
+                }
+                Hit h;
+                const bool blocked = query<VARIANT>(p.scene, p.classes, cast, so, sd, true, sclip, h);
+                shadowed = !cast || blocked;
+                if (inside || (inRange && p.frame.compact)) {
+                    p.visible[out] = shadowed ? 0 : 1;
+                }
             }
         }
     }
@@ -269,12 +427,12 @@ __global__ void assemble_kernel(const dodrt_frame f, uint32_t tilesX, const floa
     }
 }
 
-template <int MODE> cudaError_t config_for(int device, LaunchConfig *cfg)
+template <int MODE, int VARIANT> cudaError_t config_for(int device, LaunchConfig *cfg)
 {
     int sms = 0, perSm = 0;
     cudaError_t e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
     if (e != cudaSuccess) return e;
-    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, trace_kernel<MODE>, 128, 0);
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, trace_kernel<MODE, VARIANT>, 128, 0);
     if (e != cudaSuccess) return e;
     if (perSm < 1) perSm = 1;
     cfg->grid = sms * perSm; // persistent: exactly one resident wave
@@ -282,14 +440,47 @@ template <int MODE> cudaError_t config_for(int device, LaunchConfig *cfg)
     return cudaSuccess;
 }
 
-} // namespace
+template <int MODE, int VARIANT> void launch_one(const TraceParams &p, const LaunchConfig &cfg, cudaStream_t stream)
+{
+    trace_kernel<MODE, VARIANT><<<cfg.grid, cfg.block, 0, stream>>>(p);
+}
 
-cudaError_t trace_launch_config(int device, TraceMode mode, LaunchConfig *cfg)
+template <int VARIANT> cudaError_t config_mode(int device, TraceMode mode, LaunchConfig *cfg)
 {
     switch (mode) {
-    case kModeRays: return config_for<kModeRays>(device, cfg);
-    case kModePrimary: return config_for<kModePrimary>(device, cfg);
-    default: return config_for<kModeShadow>(device, cfg);
+    case kModeRays: return config_for<kModeRays, VARIANT>(device, cfg);
+    case kModePrimary: return config_for<kModePrimary, VARIANT>(device, cfg);
+    default: return config_for<kModeShadow, VARIANT>(device, cfg);
+    }
+}
+
+template <int VARIANT> void launch_mode(TraceMode mode, const TraceParams &p, const LaunchConfig &cfg, cudaStream_t stream)
+{
+    switch (mode) {
+    case kModeRays: launch_one<kModeRays, VARIANT>(p, cfg, stream); break;
+    case kModePrimary: launch_one<kModePrimary, VARIANT>(p, cfg, stream); break;
+    default: launch_one<kModeShadow, VARIANT>(p, cfg, stream); break;
+    }
+}
+
+} // namespace
+
+int default_variant()
+{
+    static const int v = [] {
+        const char *e = std::getenv("DODRT_VARIANT");
+        const int x = e ? std::atoi(e) : kDefaultVariant;
+        return (x >= 0 && x < kNumVariants) ? x : kDefaultVariant;
+    }();
+    return v;
+}
+
+cudaError_t trace_launch_config(int device, TraceMode mode, int variant, LaunchConfig *cfg)
+{
+    switch (variant) {
+    case 0: return config_mode<0>(device, mode, cfg);
+    case 1: return config_mode<1>(device, mode, cfg);
+    default: return config_mode<2>(device, mode, cfg);
     }
 }
 
@@ -297,10 +488,10 @@ cudaError_t launch_trace(TraceMode mode, const TraceParams &p, const LaunchConfi
 {
     cudaError_t e = cudaMemsetAsync(p.counter, 0, sizeof(unsigned long long), stream);
     if (e != cudaSuccess) return e;
-    switch (mode) {
-    case kModeRays: trace_kernel<kModeRays><<<cfg.grid, cfg.block, 0, stream>>>(p); break;
-    case kModePrimary: trace_kernel<kModePrimary><<<cfg.grid, cfg.block, 0, stream>>>(p); break;
-    default: trace_kernel<kModeShadow><<<cfg.grid, cfg.block, 0, stream>>>(p); break;
+    switch (p.variant) {
+    case 0: launch_mode<0>(mode, p, cfg, stream); break;
+    case 1: launch_mode<1>(mode, p, cfg, stream); break;
+    default: launch_mode<2>(mode, p, cfg, stream); break;
     }
     return cudaGetLastError();
 }

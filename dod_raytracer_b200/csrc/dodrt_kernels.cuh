@@ -10,9 +10,14 @@ enum TraceMode : int {
     kModeShadow = 2,  // in-kernel shadow ray generation      (dodrt_trace_shadow*)
 };
 
+constexpr int kNumVariants = 3;    // see the header comment of dodrt_kernels.cu
+constexpr int kDefaultVariant = 2;
+int default_variant();             // kDefaultVariant unless env DODRT_VARIANT overrides it
+
 struct TraceParams {
     DeviceScene scene;
     uint32_t classes;
+    int variant;
     // kModeRays
     const dodrt_ray *rays;
     // all modes: number of work items (rays, or result slots of the frame incl. edge padding)
@@ -35,7 +40,7 @@ struct LaunchConfig {
 };
 
 // Occupancy-derived persistent launch shape for the given device (cached by the caller).
-cudaError_t trace_launch_config(int device, TraceMode mode, LaunchConfig *cfg);
+cudaError_t trace_launch_config(int device, TraceMode mode, int variant, LaunchConfig *cfg);
 cudaError_t launch_trace(TraceMode mode, const TraceParams &p, const LaunchConfig &cfg, cudaStream_t stream);
 
 // Multi-GPU: gathered per-rank compact results -> row-major frame (one thread per pixel).

@@ -141,6 +141,10 @@ DODRT_API int dodrt_scene_set_boxes(dodrt_scene *scene, const float *box_lanes, 
 /* Config::Epsilon (config.h:9), used by the plane and cylinder tests; default 1e-4 */
 DODRT_API int dodrt_scene_set_epsilon(dodrt_scene *scene, float epsilon);
 
+/* Tuning / A-B knob: which traversal kernel variant answers the queries (all variants return identical
+ * results; see dod_raytracer_b200/csrc/dodrt_kernels.cu).  variant < 0 restores the default. */
+DODRT_API int dodrt_scene_set_kernel_variant(dodrt_scene *scene, int variant);
+
 /* ---- queries: host buffers (copies in and out are part of the call) --------------------------
  * dodrt_intersect is the batch form of `bool KDTree::intersect(_Intersect&) const` (kdtree.h:13) and
  * `static bool BaseShape<D>::intersect(_Intersect&)` (base_shape.h:23) chained as in

@@ -21,10 +21,12 @@ def sha(a):
     return hashlib.sha256(np.ascontiguousarray(a).tobytes()).hexdigest()
 
 
-@pytest.fixture(scope="module")
-def teapot():
+@pytest.fixture(scope="module", params=[0, 1, 2], ids=lambda v: f"variant{v}")
+def teapot(request):
+    """every kernel variant must return the same bits"""
     scene = teapot_scene(full=True)
     g = upload(scene)
+    g.set_kernel_variant(request.param)
     yield scene, g
     g.close()
 
