@@ -76,6 +76,7 @@ struct dodrt_scene {
     DeviceScene dev{};
     uint2 *d_nodes = nullptr;
     float4 *d_tris = nullptr;
+    float4 *d_lanes4 = nullptr;
     float *d_spheres = nullptr;
     float *d_planes = nullptr;
     dodrt_cylinder *d_cylinders = nullptr;
@@ -272,6 +273,7 @@ int dodrt_scene_destroy(dodrt_scene *s)
     if (s->pool) cudaMemPoolDestroy(s->pool);
     freeDevice(s->d_nodes);
     freeDevice(s->d_tris);
+    freeDevice(s->d_lanes4);
     freeDevice(s->d_spheres);
     freeDevice(s->d_planes);
     freeDevice(s->d_cylinders);
@@ -302,8 +304,10 @@ int dodrt_scene_set_kdtree(dodrt_scene *s, const uint64_t *nodes, uint32_t num_n
     if (!guard.ok) return fail(DODRT_E_CUDA, "cannot select device %d", s->device);
     freeDevice(s->d_nodes);
     freeDevice(s->d_tris);
+    freeDevice(s->d_lanes4);
     s->dev.nodes = nullptr;
     s->dev.tris = nullptr;
+    s->dev.lanes4 = nullptr;
     s->dev.num_nodes = 0;
     s->dev.num_tri_lanes = 0;
     if (num_nodes) {
@@ -316,7 +320,8 @@ int dodrt_scene_set_kdtree(dodrt_scene *s, const uint64_t *nodes, uint32_t num_n
         CUDA_TRY(cudaMalloc(&d_lanes, laneBytes));
         cudaError_t e = cudaMemcpy(d_lanes, tri_lanes, laneBytes, cudaMemcpyHostToDevice);
         if (e == cudaSuccess) e = cudaMalloc(&s->d_tris, (size_t)num_tri_lanes * kLane * 3 * sizeof(float4));
-        if (e == cudaSuccess) e = launch_repack_triangles(d_lanes, num_tri_lanes, s->d_tris, nullptr);
+        if (e == cudaSuccess) e = cudaMalloc(&s->d_lanes4, laneBytes);
+        if (e == cudaSuccess) e = launch_repack_triangles(d_lanes, num_tri_lanes, s->d_tris, s->d_lanes4, nullptr);
         if (e == cudaSuccess) e = cudaDeviceSynchronize();
         cudaFree(d_lanes);
         if (e != cudaSuccess) return fail(DODRT_E_CUDA, "triangle upload: %s", cudaGetErrorString(e));
@@ -324,6 +329,7 @@ int dodrt_scene_set_kdtree(dodrt_scene *s, const uint64_t *nodes, uint32_t num_n
     }
     s->dev.nodes = s->d_nodes;
     s->dev.tris = s->d_tris;
+    s->dev.lanes4 = s->d_lanes4;
     s->dev.num_nodes = num_nodes;
     s->dev.num_tri_lanes = num_tri_lanes;
     for (int i = 0; i < 3; i++) {

@@ -26,6 +26,10 @@ constexpr uint32_t kLeafFlag = 3u;
 struct DeviceScene {
     const uint2 *nodes;     // kdtree.h:16-48, 8 B each
     const float4 *tris;     // 3 x float4 per triangle slot
+    // The same data in the reference's own lane shape (triangle.h:33-44: SoA of 8, 288 B per lane) with
+    // B, C replaced by AB, AC: Ax[8] Ay[8] Az[8] ABx[8] ABy[8] ABz[8] ACx[8] ACy[8] ACz[8] = 18 float4.
+    // float4 (c*2 + h) holds component c of triangle slots 4h..4h+3.
+    const float4 *lanes4;
     uint32_t num_nodes;
     uint32_t num_tri_lanes;
     float bmin[3], bmax[3]; // KDTree::m_bounds
@@ -184,6 +188,58 @@ __device__ __forceinline__ bool triangle_test_fast(const float4 q0, const float4
     uOut = u;
     vOut = v;
     return true;
+}
+
+// First stage of triangle_test_fast for one triangle, branch-free: can this triangle still be accepted
+// after the det / u tests?  (Used four triangles at a time on the SoA lanes, see lane_half_test.)
+__device__ __forceinline__ bool triangle_may_hit(float Ax, float Ay, float Az, float ABx, float ABy, float ABz, float ACx,
+                                                 float ACy, float ACz, const float o[3], const float d[3])
+{
+    float px = d[1] * ACz - d[2] * ACy;
+    float py = d[2] * ACx - d[0] * ACz;
+    float pz = d[0] * ACy - d[1] * ACx;
+    float det = dot3(px, py, pz, ABx, ABy, ABz);
+    float tx = o[0] - Ax, ty = o[1] - Ay, tz = o[2] - Az;
+    float a = dot3(tx, ty, tz, px, py, pz);
+    const float ad = fabsf(det);
+    // (ad > 0) is the reference's |det| > 0 (NaN fails); the other two are the conservative u tests
+    return (ad > 0.0f) & !sign_differs_or_zero(a, det) & !(fabsf(a) > ad * 1.00001f);
+}
+
+// Four consecutive triangle slots (4h .. 4h+3) of one SoA lane: 9 x LDG.128, a branch-free first stage
+// for all four (independent dependency chains), and the full test -- in slot order, against the running
+// clip -- only for the survivors.  Returns true when at least one triangle was accepted.
+__device__ __forceinline__ bool lane_half_test(const float4 *__restrict__ lane, int h, uint32_t firstId, const float o[3],
+                                               const float d[3], float &clip, Hit &hit)
+{
+    const float4 Ax = __ldg(lane + 0 + h), Ay = __ldg(lane + 2 + h), Az = __ldg(lane + 4 + h);
+    const float4 Bx = __ldg(lane + 6 + h), By = __ldg(lane + 8 + h), Bz = __ldg(lane + 10 + h);
+    const float4 Cx = __ldg(lane + 12 + h), Cy = __ldg(lane + 14 + h), Cz = __ldg(lane + 16 + h);
+    const bool m0 = triangle_may_hit(Ax.x, Ay.x, Az.x, Bx.x, By.x, Bz.x, Cx.x, Cy.x, Cz.x, o, d);
+    const bool m1 = triangle_may_hit(Ax.y, Ay.y, Az.y, Bx.y, By.y, Bz.y, Cx.y, Cy.y, Cz.y, o, d);
+    const bool m2 = triangle_may_hit(Ax.z, Ay.z, Az.z, Bx.z, By.z, Bz.z, Cx.z, Cy.z, Cz.z, o, d);
+    const bool m3 = triangle_may_hit(Ax.w, Ay.w, Az.w, Bx.w, By.w, Bz.w, Cx.w, Cy.w, Cz.w, o, d);
+    if (!(m0 | m1 | m2 | m3)) {
+        return false;
+    }
+    bool any = false;
+    float t, u, v;
+#define DODRT_SLOT(k, M, c)                                                                                        \
+    if (M && triangle_test_fast(make_float4(Ax.c, Ay.c, Az.c, Bx.c), make_float4(By.c, Bz.c, Cx.c, Cy.c),          \
+                                make_float4(Cz.c, 0.0f, 0.0f, 0.0f), o, d, clip, t, u, v)) {                        \
+        clip = t;                                                                                                  \
+        hit.t = t;                                                                                                 \
+        hit.prim = (DODRT_KIND_TRIANGLE << DODRT_KIND_SHIFT) | (firstId + k);                                      \
+        hit.u = u;                                                                                                 \
+        hit.v = v;                                                                                                 \
+        any = true;                                                                                                \
+    }
+    DODRT_SLOT(0, m0, x)
+    DODRT_SLOT(1, m1, y)
+    DODRT_SLOT(2, m2, z)
+    DODRT_SLOT(3, m3, w)
+#undef DODRT_SLOT
+    return any;
 }
 
 // Sphere::intersect_impl, sphere.cpp:26-160 (lane-structured for the any-hit break, sphere.cpp:138-141)

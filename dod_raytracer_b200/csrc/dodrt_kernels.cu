@@ -16,6 +16,8 @@
 //      (8 triangles)" and always runs the phase the MAJORITY of its live rays is waiting for, so at
 //      least half of the live lanes do useful work in every instruction (profiles/r01_*: the baseline
 //      loop ran with 11.8 of 32 lanes active because rays at interior nodes waited for whole leaves).
+//   3  variant 2 on the SoA lane layout (the reference's own 288-B lanes with AB/AC precomputed): 18 instead
+//      of 24 LDG.128 per lane and a branch-free four-triangles-at-a-time first stage.
 // Every variant computes identical results (parity tests run all of them).
 #include "dodrt_kernels.cuh"
 
@@ -143,7 +145,7 @@ __device__ __forceinline__ void tree_pop(TreeState &st, const uint32_t *stackNod
     }
 }
 
-template <bool FAST>
+template <bool SOA>
 __device__ __forceinline__ bool kdtree_query_voted(const DeviceScene &s, bool enter, const float o[3], const float d[3],
                                                    bool any, float &clip, Hit &hit)
 {
@@ -174,17 +176,23 @@ __device__ __forceinline__ bool kdtree_query_voted(const DeviceScene &s, bool en
         }
         if (__popc(leafMask) >= __popc(nodeMask)) {
             if (wantLeaf) { // one reference lane = 8 consecutive triangle slots (triangle.cpp:43-140)
-                const float4 *tri = s.tris + (size_t)st.triCur * 3;
+                if (SOA) {
+                    const float4 *lane = s.lanes4 + (size_t)(st.triCur >> 3) * 18;
+                    if (lane_half_test(lane, 0, st.triCur, o, d, clip, hit)) found = true;
+                    if (!(any && found) && lane_half_test(lane, 1, st.triCur + 4, o, d, clip, hit)) found = true;
+                } else {
+                    const float4 *tri = s.tris + (size_t)st.triCur * 3;
 #pragma unroll 4
-                for (uint32_t k = 0; k < (uint32_t)kLane; k++, tri += 3) {
-                    float t, u, v;
-                    if (tri_test<FAST>(tri, o, d, clip, t, u, v)) {
-                        clip = t;
-                        hit.t = t;
-                        hit.prim = (DODRT_KIND_TRIANGLE << DODRT_KIND_SHIFT) | (st.triCur + k);
-                        hit.u = u;
-                        hit.v = v;
-                        found = true;
+                    for (uint32_t k = 0; k < (uint32_t)kLane; k++, tri += 3) {
+                        float t, u, v;
+                        if (tri_test<true>(tri, o, d, clip, t, u, v)) {
+                            clip = t;
+                            hit.t = t;
+                            hit.prim = (DODRT_KIND_TRIANGLE << DODRT_KIND_SHIFT) | (st.triCur + k);
+                            hit.u = u;
+                            hit.v = v;
+                            found = true;
+                        }
                     }
                 }
                 st.triCur += kLane;
@@ -284,8 +292,8 @@ __device__ __forceinline__ bool query(const DeviceScene &s, uint32_t classes, bo
     }
     const bool enter = !decided && (classes & DODRT_CLS_TREE);
     Hit h;
-    if (VARIANT == 2) {
-        if (kdtree_query_voted<true>(s, enter, o, d, any, clip, h)) {
+    if (VARIANT >= 2) {
+        if (kdtree_query_voted<VARIANT == 3>(s, enter, o, d, any, clip, h)) {
             hit = h;
             found = true;
         }
@@ -387,7 +395,8 @@ template <int MODE, int VARIANT> __global__ void __launch_bounds__(128) trace_ke
 }
 
 // One thread per triangle slot: gather the 9 SoA floats of slot j of lane i and emit A, AB, AC.
-__global__ void repack_triangles_kernel(const float *__restrict__ lanes, uint32_t numLanes, float4 *__restrict__ tris)
+__global__ void repack_triangles_kernel(const float *__restrict__ lanes, uint32_t numLanes, float4 *__restrict__ tris,
+                                        float *__restrict__ lanes4)
 {
     const uint64_t idx = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= (uint64_t)numLanes * kLane) {
@@ -402,6 +411,16 @@ __global__ void repack_triangles_kernel(const float *__restrict__ lanes, uint32_
     tris[idx * 3 + 0] = make_float4(Ax, Ay, Az, Bx - Ax);
     tris[idx * 3 + 1] = make_float4(By - Ay, Bz - Az, Cx - Ax, Cy - Ay);
     tris[idx * 3 + 2] = make_float4(Cz - Az, 0.0f, 0.0f, 0.0f);
+    float *out = lanes4 + (idx / kLane) * 72 + j; // SoA lane: A, AB, AC components, 8 slots each
+    out[0 * kLane] = Ax;
+    out[1 * kLane] = Ay;
+    out[2 * kLane] = Az;
+    out[3 * kLane] = Bx - Ax;
+    out[4 * kLane] = By - Ay;
+    out[5 * kLane] = Bz - Az;
+    out[6 * kLane] = Cx - Ax;
+    out[7 * kLane] = Cy - Ay;
+    out[8 * kLane] = Cz - Az;
 }
 
 // Inverse of slot_to_pixel over all ranks: pixel -> (rank, slot).  Pure data movement (16+1 B per pixel).
@@ -480,7 +499,8 @@ cudaError_t trace_launch_config(int device, TraceMode mode, int variant, LaunchC
     switch (variant) {
     case 0: return config_mode<0>(device, mode, cfg);
     case 1: return config_mode<1>(device, mode, cfg);
-    default: return config_mode<2>(device, mode, cfg);
+    case 2: return config_mode<2>(device, mode, cfg);
+    default: return config_mode<3>(device, mode, cfg);
     }
 }
 
@@ -491,7 +511,8 @@ cudaError_t launch_trace(TraceMode mode, const TraceParams &p, const LaunchConfi
     switch (p.variant) {
     case 0: launch_mode<0>(mode, p, cfg, stream); break;
     case 1: launch_mode<1>(mode, p, cfg, stream); break;
-    default: launch_mode<2>(mode, p, cfg, stream); break;
+    case 2: launch_mode<2>(mode, p, cfg, stream); break;
+    default: launch_mode<3>(mode, p, cfg, stream); break;
     }
     return cudaGetLastError();
 }
@@ -508,13 +529,14 @@ cudaError_t launch_assemble(const dodrt_frame &frame, uint32_t tiles_x, const do
     return cudaGetLastError();
 }
 
-cudaError_t launch_repack_triangles(const float *d_lanes, uint32_t num_lanes, float4 *d_tris, cudaStream_t stream)
+cudaError_t launch_repack_triangles(const float *d_lanes, uint32_t num_lanes, float4 *d_tris, float4 *d_lanes4,
+                                    cudaStream_t stream)
 {
     const uint64_t n = (uint64_t)num_lanes * kLane;
     if (n == 0) return cudaSuccess;
     const int block = 256;
     const unsigned grid = (unsigned)((n + block - 1) / block);
-    repack_triangles_kernel<<<grid, block, 0, stream>>>(d_lanes, num_lanes, d_tris);
+    repack_triangles_kernel<<<grid, block, 0, stream>>>(d_lanes, num_lanes, d_tris, reinterpret_cast<float *>(d_lanes4));
     return cudaGetLastError();
 }
 

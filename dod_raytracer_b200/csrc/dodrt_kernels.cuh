@@ -10,7 +10,7 @@ enum TraceMode : int {
     kModeShadow = 2,  // in-kernel shadow ray generation      (dodrt_trace_shadow*)
 };
 
-constexpr int kNumVariants = 3;    // see the header comment of dodrt_kernels.cu
+constexpr int kNumVariants = 4;    // see the header comment of dodrt_kernels.cu
 constexpr int kDefaultVariant = 2;
 int default_variant();             // kDefaultVariant unless env DODRT_VARIANT overrides it
 
@@ -49,6 +49,7 @@ cudaError_t launch_assemble(const dodrt_frame &frame, uint32_t tiles_x, const do
                             cudaStream_t stream);
 
 // Upload helper: reference lanes (288 B, SoA of 8) -> per-triangle 48-B records with AB/AC.
-cudaError_t launch_repack_triangles(const float *d_lanes, uint32_t num_lanes, float4 *d_tris, cudaStream_t stream);
+cudaError_t launch_repack_triangles(const float *d_lanes, uint32_t num_lanes, float4 *d_tris, float4 *d_lanes4,
+                                    cudaStream_t stream);
 
 } // namespace dodrt
