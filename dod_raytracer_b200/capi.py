@@ -14,7 +14,7 @@ from typing import Optional
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libdodrt_cuda.so")
+LIB_PATH = os.environ.get("DODRT_LIB") or os.path.join(_HERE, "lib", "libdodrt_cuda.so")
 
 # include/dodrt.h structs
 RAY_DT = np.dtype([("o", "<f4", 3), ("d", "<f4", 3), ("clip", "<f4"), ("flags", "<u4")])

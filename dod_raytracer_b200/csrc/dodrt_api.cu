@@ -10,6 +10,7 @@
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 #include <new>
@@ -248,6 +249,12 @@ int dodrt_scene_create(int device, dodrt_scene **scene)
     if (!s) return fail(DODRT_E_NOMEM, "out of host memory");
     s->device = device;
     s->dev.epsilon = 0.0001f; // Config::Epsilon default, config.h:9
+    {
+        const char *t = std::getenv("DODRT_TUNE"); // "num,den,maxNodeRun" (exploration knob)
+        unsigned a = 3, b = 1, c = 0xFFFFFFFFu; // measured best on dragon4k (profiles/r01_vote_rule_sweep.txt)
+        if (t) std::sscanf(t, "%u,%u,%u", &a, &b, &c);
+        s->dev.tune[0] = a, s->dev.tune[1] = b, s->dev.tune[2] = c, s->dev.tune[3] = 0;
+    }
     cudaError_t e = cudaMalloc(&s->d_counters, sizeof(unsigned long long) * kCounterSlots);
     s->variant = default_variant();
     for (int v = 0; v < kNumVariants; v++) {

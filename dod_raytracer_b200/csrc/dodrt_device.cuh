@@ -42,6 +42,9 @@ struct DeviceScene {
     const float *box_lanes;    // minx miny minz maxx maxy maxz [8]
     uint32_t num_boxes;
     float epsilon;
+    // traversal scheduling knobs (dodrt_kernels.cu): leaf phase runs when nLeaf*tune[1] >= nNode*tune[0], or after
+    // tune[2] consecutive node phases
+    uint32_t tune[4];
 };
 
 struct Hit {

@@ -18,6 +18,9 @@
 //      loop ran with 11.8 of 32 lanes active because rays at interior nodes waited for whole leaves).
 //   3  variant 2 on the SoA lane layout (the reference's own 288-B lanes with AB/AC precomputed): 18 instead
 //      of 24 LDG.128 per lane and a branch-free four-triangles-at-a-time first stage.
+//   4  variant 3 plus warp-level regrouping: analytic classes + bounds test for 32 fresh rays at a time, the
+//      survivors compacted (ballot/popc) into a per-warp pool in shared memory from which idle lanes are
+//      refilled (dodrt_pool_kernel.inl).
 // Every variant computes identical results (parity tests run all of them).
 #include "dodrt_kernels.cuh"
 
@@ -145,11 +148,83 @@ __device__ __forceinline__ void tree_pop(TreeState &st, const uint32_t *stackNod
     }
 }
 
+// One triangle lane (8 consecutive slots, triangle.cpp:43-140) of the leaf this ray is in.
 template <bool SOA>
-__device__ __forceinline__ bool kdtree_query_voted(const DeviceScene &s, bool enter, const float o[3], const float d[3],
-                                                   bool any, float &clip, Hit &hit)
+__device__ __forceinline__ void leaf_step(const DeviceScene &s, TreeState &st, const float o[3], const float d[3], bool any,
+                                          float &clip, Hit &hit, bool &found, const uint32_t *stackNode,
+                                          const float *stackTmin, const float *stackTmax)
 {
-    TreeState st;
+    if (SOA) {
+        const float4 *lane = s.lanes4 + (size_t)(st.triCur >> 3) * 18;
+        if (lane_half_test(lane, 0, st.triCur, o, d, clip, hit)) found = true;
+        if (!(any && found) && lane_half_test(lane, 1, st.triCur + 4, o, d, clip, hit)) found = true;
+    } else {
+        const float4 *tri = s.tris + (size_t)st.triCur * 3;
+#pragma unroll 4
+        for (uint32_t k = 0; k < (uint32_t)kLane; k++, tri += 3) {
+            float t, u, v;
+            if (tri_test<true>(tri, o, d, clip, t, u, v)) {
+                clip = t;
+                hit.t = t;
+                hit.prim = (DODRT_KIND_TRIANGLE << DODRT_KIND_SHIFT) | (st.triCur + k);
+                hit.u = u;
+                hit.v = v;
+                found = true;
+            }
+        }
+    }
+    st.triCur += kLane;
+    if (any && found) {
+        st.live = false; // kdtree.cpp:338-341
+    } else if (st.triCur == st.triEnd) {
+        tree_pop(st, stackNode, stackTmin, stackTmax);
+    }
+}
+
+// One kd node visit (one iteration of the reference's while loop, kdtree.cpp:284-333,347-357).
+__device__ __forceinline__ void node_step(const DeviceScene &s, TreeState &st, const float o[3], const float d[3],
+                                          float clip, uint32_t *stackNode, float *stackTmin, float *stackTmax)
+{
+    if (clip < st.tmin) { // kdtree.cpp:286-289
+        st.live = false;
+        return;
+    }
+    const uint2 n = __ldg(&s.nodes[st.node]);
+    if ((n.x & 3u) != kLeafFlag) {
+        const uint32_t axis = n.x & 3u;
+        const float split = __uint_as_float(n.y);
+        const float oa = pick(o, axis);
+        const float tPlane = (split - oa) * pick(st.inv, axis); // kdtree.cpp:293
+        const bool leftFirst = (oa < split) || (oa == split && pick(d, axis) <= 0.0f); // kdtree.cpp:297-299
+        const uint32_t below = st.node + 1, above = n.x >> 2;
+        const uint32_t nearChild = leftFirst ? below : above;
+        const uint32_t farChild = leftFirst ? above : below;
+        if (tPlane > st.tmax || tPlane <= 0.0f) { // kdtree.cpp:312
+            st.node = nearChild;
+        } else if (tPlane < st.tmin) { // kdtree.cpp:316
+            st.node = farChild;
+        } else { // kdtree.cpp:320-329
+            stackNode[st.sp] = farChild;
+            stackTmin[st.sp] = tPlane;
+            stackTmax[st.sp] = st.tmax;
+            ++st.sp;
+            st.node = nearChild;
+            st.tmax = tPlane;
+        }
+    } else {
+        const uint32_t numTris = (n.x >> 2) * kLane;
+        if (numTris == 0) {
+            tree_pop(st, stackNode, stackTmin, stackTmax);
+        } else {
+            st.triCur = n.y * kLane;
+            st.triEnd = st.triCur + numTris;
+        }
+    }
+}
+
+__device__ __forceinline__ void tree_enter(const DeviceScene &s, TreeState &st, bool enter, const float o[3], const float d[3],
+                                           float clip)
+{
     st.live = false;
     st.triCur = st.triEnd = 0;
     st.sp = 0;
@@ -162,10 +237,86 @@ __device__ __forceinline__ bool kdtree_query_voted(const DeviceScene &s, bool en
         st.inv[2] = 1.0f / d[2];
         st.live = slab(s.bmin, s.bmax, o, st.inv, clip, st.tmin, st.tmax) && !(st.tmin > clip); // kdtree.cpp:274
     }
+}
+
+// Leaf phase with at most 16 rays waiting for triangles: the 32 lanes of the warp become 16 pairs, pair r
+// serves the r-th waiting ray, lane 2r tests slots 0..3 and lane 2r+1 slots 4..7 of that ray's current triangle
+// lane (ray and lane pointer travel by shuffle), and the owner merges the two answers in slot order: the
+// second half is accepted only if its t beats the clip left by the first half (strict <), which is exactly
+// the sequential result because each half already holds its own (t, id)-minimum below the incoming clip.
+__device__ __forceinline__ void leaf_step_shared(const DeviceScene &s, TreeState &st, unsigned leafMask, bool wantLeaf,
+                                                 const float o[3], const float d[3], bool any, float &clip, Hit &hit,
+                                                 bool &found, const uint32_t *stackNode, const float *stackTmin,
+                                                 const float *stackTmax)
+{
+    __shared__ uint8_t ownerOfRank[8][16]; // up to 8 warps per block
+    const uint32_t lane = threadIdx.x & 31u;
+    uint8_t *table = ownerOfRank[(threadIdx.x >> 5) & 7u];
+    const uint32_t myRank = __popc(leafMask & ((1u << lane) - 1u));
+    if (wantLeaf) {
+        table[myRank] = (uint8_t)lane;
+    }
+    __syncwarp();
+    const uint32_t nLeaf = __popc(leafMask);
+    const uint32_t unitRank = lane >> 1, half = lane & 1u;
+    const bool unitValid = unitRank < nLeaf;
+    const uint32_t owner = unitValid ? table[unitRank] : lane;
+    __syncwarp();
+    // ray of the owner
+    float ro[3], rd[3];
+    ro[0] = __shfl_sync(0xffffffffu, o[0], owner);
+    ro[1] = __shfl_sync(0xffffffffu, o[1], owner);
+    ro[2] = __shfl_sync(0xffffffffu, o[2], owner);
+    rd[0] = __shfl_sync(0xffffffffu, d[0], owner);
+    rd[1] = __shfl_sync(0xffffffffu, d[1], owner);
+    rd[2] = __shfl_sync(0xffffffffu, d[2], owner);
+    float rclip = __shfl_sync(0xffffffffu, clip, owner);
+    const uint32_t rtri = __shfl_sync(0xffffffffu, st.triCur, owner);
+    Hit uh;
+    uh.t = 0.0f, uh.prim = DODRT_MISS, uh.u = uh.v = 0.0f;
+    bool uacc = false;
+    if (unitValid) {
+        const float4 *lanePtr = s.lanes4 + (size_t)(rtri >> 3) * 18;
+        uacc = lane_half_test(lanePtr, (int)half, rtri + 4u * half, ro, rd, rclip, uh);
+    }
+    // owners collect the answers of their two units
+    const uint32_t src0 = wantLeaf ? 2u * myRank : lane, src1 = wantLeaf ? 2u * myRank + 1u : lane;
+    const unsigned accMask = __ballot_sync(0xffffffffu, uacc);
+    const float t0 = __shfl_sync(0xffffffffu, uh.t, src0), t1 = __shfl_sync(0xffffffffu, uh.t, src1);
+    const float u0 = __shfl_sync(0xffffffffu, uh.u, src0), u1 = __shfl_sync(0xffffffffu, uh.u, src1);
+    const float v0 = __shfl_sync(0xffffffffu, uh.v, src0), v1 = __shfl_sync(0xffffffffu, uh.v, src1);
+    const uint32_t p0 = __shfl_sync(0xffffffffu, uh.prim, src0), p1 = __shfl_sync(0xffffffffu, uh.prim, src1);
+    if (wantLeaf) {
+        if ((accMask >> src0) & 1u) {
+            clip = t0;
+            hit.t = t0, hit.prim = p0, hit.u = u0, hit.v = v0;
+            found = true;
+        }
+        if (((accMask >> src1) & 1u) && t1 < clip) {
+            clip = t1;
+            hit.t = t1, hit.prim = p1, hit.u = u1, hit.v = v1;
+            found = true;
+        }
+        st.triCur += kLane;
+        if (any && found) {
+            st.live = false; // kdtree.cpp:338-341
+        } else if (st.triCur == st.triEnd) {
+            tree_pop(st, stackNode, stackTmin, stackTmax);
+        }
+    }
+}
+
+template <bool SOA, bool SHARE>
+__device__ __forceinline__ bool kdtree_query_voted(const DeviceScene &s, bool enter, const float o[3], const float d[3],
+                                                   bool any, float &clip, Hit &hit)
+{
+    TreeState st;
+    tree_enter(s, st, enter, o, d, clip);
     uint32_t stackNode[kMaxStack];
     float stackTmin[kMaxStack];
     float stackTmax[kMaxStack];
     bool found = false;
+    uint32_t nodeRun = 0;
     for (;;) {
         const bool wantLeaf = st.live && st.triCur < st.triEnd;
         const bool wantNode = st.live && !wantLeaf;
@@ -174,69 +325,18 @@ __device__ __forceinline__ bool kdtree_query_voted(const DeviceScene &s, bool en
         if ((leafMask | nodeMask) == 0u) {
             break;
         }
-        if (__popc(leafMask) >= __popc(nodeMask)) {
-            if (wantLeaf) { // one reference lane = 8 consecutive triangle slots (triangle.cpp:43-140)
-                if (SOA) {
-                    const float4 *lane = s.lanes4 + (size_t)(st.triCur >> 3) * 18;
-                    if (lane_half_test(lane, 0, st.triCur, o, d, clip, hit)) found = true;
-                    if (!(any && found) && lane_half_test(lane, 1, st.triCur + 4, o, d, clip, hit)) found = true;
-                } else {
-                    const float4 *tri = s.tris + (size_t)st.triCur * 3;
-#pragma unroll 4
-                    for (uint32_t k = 0; k < (uint32_t)kLane; k++, tri += 3) {
-                        float t, u, v;
-                        if (tri_test<true>(tri, o, d, clip, t, u, v)) {
-                            clip = t;
-                            hit.t = t;
-                            hit.prim = (DODRT_KIND_TRIANGLE << DODRT_KIND_SHIFT) | (st.triCur + k);
-                            hit.u = u;
-                            hit.v = v;
-                            found = true;
-                        }
-                    }
-                }
-                st.triCur += kLane;
-                if (any && found) {
-                    st.live = false; // kdtree.cpp:338-341
-                } else if (st.triCur == st.triEnd) {
-                    tree_pop(st, stackNode, stackTmin, stackTmax);
-                }
+        const uint32_t nLeaf = __popc(leafMask), nNode = __popc(nodeMask);
+        if (nNode == 0u || (nLeaf != 0u && (nLeaf * s.tune[1] >= nNode * s.tune[0] || nodeRun >= s.tune[2]))) {
+            nodeRun = 0;
+            if (SHARE && nLeaf <= 16u) {
+                leaf_step_shared(s, st, leafMask, wantLeaf, o, d, any, clip, hit, found, stackNode, stackTmin, stackTmax);
+            } else if (wantLeaf) {
+                leaf_step<SOA>(s, st, o, d, any, clip, hit, found, stackNode, stackTmin, stackTmax);
             }
-        } else if (wantNode) {
-            if (clip < st.tmin) { // kdtree.cpp:286-289
-                st.live = false;
-            } else {
-                const uint2 n = __ldg(&s.nodes[st.node]);
-                if ((n.x & 3u) != kLeafFlag) {
-                    const uint32_t axis = n.x & 3u;
-                    const float split = __uint_as_float(n.y);
-                    const float oa = pick(o, axis);
-                    const float tPlane = (split - oa) * pick(st.inv, axis);
-                    const bool leftFirst = (oa < split) || (oa == split && pick(d, axis) <= 0.0f);
-                    const uint32_t below = st.node + 1, above = n.x >> 2;
-                    const uint32_t nearChild = leftFirst ? below : above;
-                    const uint32_t farChild = leftFirst ? above : below;
-                    if (tPlane > st.tmax || tPlane <= 0.0f) {
-                        st.node = nearChild;
-                    } else if (tPlane < st.tmin) {
-                        st.node = farChild;
-                    } else {
-                        stackNode[st.sp] = farChild;
-                        stackTmin[st.sp] = tPlane;
-                        stackTmax[st.sp] = st.tmax;
-                        ++st.sp;
-                        st.node = nearChild;
-                        st.tmax = tPlane;
-                    }
-                } else {
-                    const uint32_t numTris = (n.x >> 2) * kLane;
-                    if (numTris == 0) {
-                        tree_pop(st, stackNode, stackTmin, stackTmax);
-                    } else {
-                        st.triCur = n.y * kLane;
-                        st.triEnd = st.triCur + numTris;
-                    }
-                }
+        } else {
+            ++nodeRun;
+            if (wantNode) {
+                node_step(s, st, o, d, clip, stackNode, stackTmin, stackTmax);
             }
         }
     }
@@ -293,7 +393,7 @@ __device__ __forceinline__ bool query(const DeviceScene &s, uint32_t classes, bo
     const bool enter = !decided && (classes & DODRT_CLS_TREE);
     Hit h;
     if (VARIANT >= 2) {
-        if (kdtree_query_voted<VARIANT == 3>(s, enter, o, d, any, clip, h)) {
+        if (kdtree_query_voted<VARIANT >= 3, VARIANT == 5>(s, enter, o, d, any, clip, h)) {
             hit = h;
             found = true;
         }
@@ -322,7 +422,10 @@ __device__ __forceinline__ bool slot_to_pixel(const dodrt_frame &f, uint32_t til
     return col < f.width && row < f.height;
 }
 
-template <int MODE, int VARIANT> __global__ void __launch_bounds__(128) trace_kernel(const TraceParams p)
+#ifndef DODRT_MINBLOCKS
+#define DODRT_MINBLOCKS 1
+#endif
+template <int MODE, int VARIANT> __global__ void __launch_bounds__(128, DODRT_MINBLOCKS) trace_kernel(const TraceParams p)
 {
     const uint32_t lane = threadIdx.x & 31u;
     for (;;) {
@@ -394,6 +497,8 @@ template <int MODE, int VARIANT> __global__ void __launch_bounds__(128) trace_ke
     }
 }
 
+#include "dodrt_pool_kernel.inl"
+
 // One thread per triangle slot: gather the 9 SoA floats of slot j of lane i and emit A, AB, AC.
 __global__ void repack_triangles_kernel(const float *__restrict__ lanes, uint32_t numLanes, float4 *__restrict__ tris,
                                         float *__restrict__ lanes4)
@@ -451,7 +556,11 @@ template <int MODE, int VARIANT> cudaError_t config_for(int device, LaunchConfig
     int sms = 0, perSm = 0;
     cudaError_t e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
     if (e != cudaSuccess) return e;
-    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, trace_kernel<MODE, VARIANT>, 128, 0);
+    if constexpr (VARIANT == 4) {
+        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, trace_kernel_pool<MODE>, 128, 0);
+    } else {
+        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, trace_kernel<MODE, VARIANT>, 128, 0);
+    }
     if (e != cudaSuccess) return e;
     if (perSm < 1) perSm = 1;
     cfg->grid = sms * perSm; // persistent: exactly one resident wave
@@ -461,7 +570,11 @@ template <int MODE, int VARIANT> cudaError_t config_for(int device, LaunchConfig
 
 template <int MODE, int VARIANT> void launch_one(const TraceParams &p, const LaunchConfig &cfg, cudaStream_t stream)
 {
-    trace_kernel<MODE, VARIANT><<<cfg.grid, cfg.block, 0, stream>>>(p);
+    if constexpr (VARIANT == 4) {
+        trace_kernel_pool<MODE><<<cfg.grid, cfg.block, 0, stream>>>(p);
+    } else {
+        trace_kernel<MODE, VARIANT><<<cfg.grid, cfg.block, 0, stream>>>(p);
+    }
 }
 
 template <int VARIANT> cudaError_t config_mode(int device, TraceMode mode, LaunchConfig *cfg)
@@ -500,7 +613,9 @@ cudaError_t trace_launch_config(int device, TraceMode mode, int variant, LaunchC
     case 0: return config_mode<0>(device, mode, cfg);
     case 1: return config_mode<1>(device, mode, cfg);
     case 2: return config_mode<2>(device, mode, cfg);
-    default: return config_mode<3>(device, mode, cfg);
+    case 3: return config_mode<3>(device, mode, cfg);
+    case 4: return config_mode<4>(device, mode, cfg);
+    default: return config_mode<5>(device, mode, cfg);
     }
 }
 
@@ -512,7 +627,9 @@ cudaError_t launch_trace(TraceMode mode, const TraceParams &p, const LaunchConfi
     case 0: launch_mode<0>(mode, p, cfg, stream); break;
     case 1: launch_mode<1>(mode, p, cfg, stream); break;
     case 2: launch_mode<2>(mode, p, cfg, stream); break;
-    default: launch_mode<3>(mode, p, cfg, stream); break;
+    case 3: launch_mode<3>(mode, p, cfg, stream); break;
+    case 4: launch_mode<4>(mode, p, cfg, stream); break;
+    default: launch_mode<5>(mode, p, cfg, stream); break;
     }
     return cudaGetLastError();
 }

@@ -10,8 +10,8 @@ enum TraceMode : int {
     kModeShadow = 2,  // in-kernel shadow ray generation      (dodrt_trace_shadow*)
 };
 
-constexpr int kNumVariants = 4;    // see the header comment of dodrt_kernels.cu
-constexpr int kDefaultVariant = 2;
+constexpr int kNumVariants = 6;    // see the header comment of dodrt_kernels.cu
+constexpr int kDefaultVariant = 3;
 int default_variant();             // kDefaultVariant unless env DODRT_VARIANT overrides it
 
 struct TraceParams {
