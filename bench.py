@@ -185,7 +185,7 @@ def run_reference_arm(args, w, mesh_files, host_arrays_fn):
 # ---- the GPU arm ---------------------------------------------------------------------------------------------
 def main():
     args = parse_args()
-    from dod_raytracer_b200 import capi, host, workloads
+    from dod_raytracer_b200 import capi, distributed, host, workloads
     w = workloads.WORKLOADS[args.workload]
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -214,10 +214,9 @@ def main():
     scene = hs.upload(local_rank)
     sizes = hs.sizes()
     tile = tuple(int(x) for x in args.tile.split("x"))
-    frame = capi.Frame.make(w.width, w.height, classes=w.classes, tile=tile, first_tile=rank, tile_stride=world,
-                            compact=1 if world > 1 else 0)
+    frame = distributed.rank_frame(w.width, w.height, w.classes, rank, world, tile)
     slots = capi.frame_local_pixels(frame) if world > 1 else w.pixels
-    slots_rank0 = capi.frame_local_pixels(capi.Frame.make(w.width, w.height, tile=tile, tile_stride=world, compact=1))
+    slots_rank0 = distributed.slots_per_rank(w.width, w.height, world, tile)
     xs, ys = host.ray_tables(w.width, w.height)
     d_xs, d_ys = torch.from_numpy(xs).to(dev), torch.from_numpy(ys).to(dev)
     lights = np.array(w.lights, np.float32)
@@ -248,8 +247,8 @@ def main():
         if ev:
             ev[2].record(stream)
         if world > 1:
-            dist.gather(d_hits, list(g_hits.unbind(0)) if rank == 0 else None, dst=0)
-            dist.gather(d_vis[0], list(g_vis.unbind(0)) if rank == 0 else None, dst=0)
+            distributed.gather_to_rank0(d_hits, world, rank, g_hits if rank == 0 else None)
+            distributed.gather_to_rank0(d_vis[0], world, rank, g_vis if rank == 0 else None)
             if rank == 0:
                 scene.frame_assemble_device(frame, g_hits.data_ptr(), g_vis.data_ptr(), slots_rank0, f_hits.data_ptr(),
                                             f_vis.data_ptr(), sp)
