@@ -90,6 +90,7 @@ struct dodrt_scene {
     uint32_t treeDepth = 0;
     std::mutex mutex; // guards scene mutation and the lazily created staging stream
     cudaStream_t stream = nullptr;
+    cudaStream_t copyStream = nullptr; // D2H of finished bands while the next band is traced
     // staging memory of the host-buffer entry points: a private pool that keeps freed blocks cached
     // (release threshold = max), so a per-frame call does not pay for physical allocation every time
     cudaMemPool_t pool = nullptr;
@@ -178,6 +179,9 @@ int ensureStream(dodrt_scene *s)
     if (!s->stream) {
         CUDA_TRY(cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking));
     }
+    if (!s->copyStream) {
+        CUDA_TRY(cudaStreamCreateWithFlags(&s->copyStream, cudaStreamNonBlocking));
+    }
     if (!s->pool) {
         cudaMemPoolProps props{};
         props.allocType = cudaMemAllocationTypePinned;
@@ -191,8 +195,11 @@ int ensureStream(dodrt_scene *s)
     return DODRT_OK;
 }
 
+// Traces local tiles [tileBegin, tileBegin + tileCount) of the frame (tileCount is clamped); d_hits / d_visible
+// always point at slot 0 of the call's result buffers.
 int launchFrame(dodrt_scene *s, TraceMode mode, const dodrt_frame *frame, const float *d_xs, const float *d_ys,
-                dodrt_hit *d_hits, const float *light, uint8_t *d_visible, cudaStream_t stream)
+                dodrt_hit *d_hits, const float *light, uint8_t *d_visible, cudaStream_t stream, uint32_t tileBegin = 0,
+                uint32_t tileCount = 0xFFFFFFFFu)
 {
     TraceParams p{};
     p.scene = s->dev;
@@ -200,11 +207,18 @@ int launchFrame(dodrt_scene *s, TraceMode mode, const dodrt_frame *frame, const 
     p.frame = *frame;
     uint32_t localTiles;
     frameTiles(frame, &p.tiles_x, &localTiles);
-    p.count = (uint64_t)localTiles * frame->tile_w * frame->tile_h;
-    p.hits = d_hits;
+    if (tileBegin >= localTiles) {
+        return DODRT_OK;
+    }
+    const uint32_t tiles = tileCount < localTiles - tileBegin ? tileCount : localTiles - tileBegin;
+    const uint64_t tilePixels = (uint64_t)frame->tile_w * frame->tile_h;
+    const uint64_t slotBase = frame->compact ? tileBegin * tilePixels : 0; // full-frame results are indexed by pixel
+    p.frame.first_tile = frame->first_tile + tileBegin * frame->tile_stride;
+    p.count = tiles * tilePixels;
+    p.hits = d_hits + slotBase;
     p.xs = d_xs;
     p.ys = d_ys;
-    p.visible = d_visible;
+    p.visible = d_visible ? d_visible + slotBase : nullptr;
     if (light) {
         p.light[0] = light[0];
         p.light[1] = light[1];
@@ -277,6 +291,7 @@ int dodrt_scene_destroy(dodrt_scene *s)
     DeviceGuard guard(s->device);
     cudaDeviceSynchronize();
     if (s->stream) cudaStreamDestroy(s->stream);
+    if (s->copyStream) cudaStreamDestroy(s->copyStream);
     if (s->pool) cudaMemPoolDestroy(s->pool);
     freeDevice(s->d_nodes);
     freeDevice(s->d_tris);
@@ -560,23 +575,73 @@ int dodrt_trace_frame(dodrt_scene *s, const dodrt_frame *frame, const float *xs,
         e = cudaMemsetAsync(d_hits, 0xFF, slots * sizeof(dodrt_hit), st);
         if (e == cudaSuccess && num_lights) e = cudaMemsetAsync(d_vis, 0, slots * (size_t)num_lights, st);
     }
+    // Copies run on a second stream so that they hide behind kernels instead of following them:
+    //  * with shadow passes, the primary hit records (16 of the 17 B per pixel) go to the host WHILE the shadow
+    //    kernels -- which only read them -- run; each light's visibility bytes follow their own pass;
+    //  * a primary-only frame is traced in `bands` bands (whole tile rows for full-frame results, runs of local
+    //    tiles for compact results, so a band's results are contiguous) and band k is copied while band k+1 is
+    //    traced.  More bands cost ~0.2 ms each in launch/tail overhead (profiles/r01_e2e_bands.txt), hence 2.
+    std::vector<cudaEvent_t> events;
+    auto fence = [&](cudaStream_t from, cudaStream_t to) -> cudaError_t { // `to` waits for what `from` has queued
+        cudaEvent_t ev = nullptr;
+        cudaError_t err = cudaEventCreateWithFlags(&ev, cudaEventDisableTiming);
+        if (err != cudaSuccess) return err;
+        events.push_back(ev);
+        err = cudaEventRecord(ev, from);
+        return err == cudaSuccess ? cudaStreamWaitEvent(to, ev, 0) : err;
+    };
     if (e == cudaSuccess) {
-        rc = launchFrame(s, kModePrimary, frame, d_tables, d_tables + frame->width, d_hits, nullptr, nullptr, st);
-        for (uint32_t l = 0; l < num_lights && rc == DODRT_OK; l++) {
-            rc = launchFrame(s, kModeShadow, frame, d_tables, d_tables + frame->width, d_hits, lights + 3 * l,
-                             d_vis + slots * l, st);
+        uint32_t tilesX, localTiles;
+        frameTiles(frame, &tilesX, &localTiles);
+        const uint64_t tilePixels = (uint64_t)frame->tile_w * frame->tile_h;
+        const bool bandable = num_lights == 0 && (frame->compact || frame->tile_stride == 1) && slots >= (1u << 19);
+        uint32_t bandTiles = localTiles;
+        if (bandable) {
+            static const uint32_t bands = [] {
+                const char *b = std::getenv("DODRT_BANDS");
+                const int v = b ? std::atoi(b) : 2;
+                return (uint32_t)(v > 0 ? v : 2);
+            }();
+            bandTiles = (localTiles + bands - 1) / bands;
+            if (!frame->compact) bandTiles = ((bandTiles + tilesX - 1) / tilesX) * tilesX; // whole tile rows
         }
-        if (rc == DODRT_OK) {
-            e = cudaMemcpyAsync(hits, d_hits, slots * sizeof(dodrt_hit), cudaMemcpyDeviceToHost, st);
-            if (e == cudaSuccess && num_lights) {
-                e = cudaMemcpyAsync(visible, d_vis, slots * (size_t)num_lights, cudaMemcpyDeviceToHost, st);
+        for (uint32_t begin = 0; begin < localTiles && rc == DODRT_OK && e == cudaSuccess; begin += bandTiles) {
+            const uint32_t count = bandTiles < localTiles - begin ? bandTiles : localTiles - begin;
+            rc = launchFrame(s, kModePrimary, frame, d_tables, d_tables + frame->width, d_hits, nullptr, nullptr, st, begin,
+                             count);
+            if (rc != DODRT_OK) break;
+            uint64_t lo = 0, hi = slots; // result range of this band
+            if (bandable && frame->compact) {
+                lo = begin * tilePixels;
+                hi = (begin + (uint64_t)count) * tilePixels;
+            } else if (bandable) {
+                lo = (uint64_t)(begin / tilesX) * frame->tile_h * frame->width;
+                hi = (uint64_t)((begin + count) / tilesX) * frame->tile_h * frame->width;
+                if (begin + count >= localTiles || hi > slots) hi = slots;
+            }
+            e = fence(st, s->copyStream);
+            if (e == cudaSuccess) {
+                e = cudaMemcpyAsync(hits + lo, d_hits + lo, (hi - lo) * sizeof(dodrt_hit), cudaMemcpyDeviceToHost, s->copyStream);
             }
         }
+        for (uint32_t l = 0; l < num_lights && rc == DODRT_OK && e == cudaSuccess; l++) {
+            rc = launchFrame(s, kModeShadow, frame, d_tables, d_tables + frame->width, d_hits, lights + 3 * l,
+                             d_vis + slots * l, st);
+            if (rc != DODRT_OK) break;
+            e = fence(st, s->copyStream);
+            if (e == cudaSuccess) {
+                e = cudaMemcpyAsync(visible + slots * l, d_vis + slots * l, slots, cudaMemcpyDeviceToHost, s->copyStream);
+            }
+        }
+        // the staging buffers are released on the compute stream: make it wait for the copies
+        if (e == cudaSuccess) e = fence(s->copyStream, st);
     }
+    if (e != cudaSuccess || rc != DODRT_OK) cudaStreamSynchronize(s->copyStream);
     if (d_tables) cudaFreeAsync(d_tables, st);
     if (d_hits) cudaFreeAsync(d_hits, st);
     if (d_vis) cudaFreeAsync(d_vis, st);
     cudaError_t es = cudaStreamSynchronize(st);
+    for (cudaEvent_t ev : events) cudaEventDestroy(ev);
     if (rc != DODRT_OK) return rc;
     if (e == cudaSuccess) e = es;
     if (e != cudaSuccess) return fail(DODRT_E_CUDA, "dodrt_trace_frame: %s", cudaGetErrorString(e));

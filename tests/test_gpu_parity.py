@@ -127,6 +127,38 @@ def test_tile_split_is_byte_identical_to_single_gpu(teapot, oracle):
         assert hits.tobytes() == full.tobytes() and vis.tobytes() == fvis.tobytes()
 
 
+def test_banded_host_path_at_1080p(teapot, oracle):
+    """dodrt_trace_frame copies results band by band while the next band is traced: full-frame bands (whole
+    tile rows) and compact bands (runs of local tiles) must reproduce the un-banded device path exactly."""
+    import torch
+    _, g = teapot
+    w, h = 1920, 1080
+    xs, ys = oracle.ray_tables(w, h)
+    dev = torch.device("cuda:0")
+    d_xs, d_ys = torch.from_numpy(xs).to(dev), torch.from_numpy(ys).to(dev)
+    d_hits = torch.empty((w * h, 16), dtype=torch.uint8, device=dev)
+    d_vis = torch.zeros(w * h, dtype=torch.uint8, device=dev)
+    frame = capi.Frame.make(w, h, classes=ALL)
+    g.trace_primary_device(frame, d_xs.data_ptr(), d_ys.data_ptr(), d_hits.data_ptr())
+    g.trace_shadow_device(frame, d_xs.data_ptr(), d_ys.data_ptr(), d_hits.data_ptr(), LIGHT0, d_vis.data_ptr())
+    torch.cuda.synchronize()
+    want_h, want_v = d_hits.cpu().numpy().tobytes(), d_vis.cpu().numpy().tobytes()
+    lights = np.stack([LIGHT0, np.array([4.0, 4.3, 3.3], np.float32)])  # lights[0], lights[1] of main.cpp:284-285
+    hits, vis = g.trace_frame(frame, xs, ys, lights)
+    assert hits.tobytes() == want_h and vis[0].tobytes() == want_v
+    assert vis[1].sum() > 0 and vis[1].tobytes() != vis[0].tobytes()
+    full_h = np.frombuffer(want_h, capi.HIT_DT)
+    for world in (2,):
+        for rank in range(world):
+            f = capi.Frame.make(w, h, classes=ALL, first_tile=rank, tile_stride=world, compact=1)
+            m = capi.frame_pixel_map(f)
+            lh, lv = g.trace_frame(f, xs, ys, LIGHT0[None, :])
+            ok = m != 0xFFFFFFFF
+            assert lh[ok].tobytes() == full_h[m[ok]].tobytes()
+            assert lv[0][ok].tobytes() == np.frombuffer(want_v, np.uint8)[m[ok]].tobytes()
+            assert (lh["prim"][~ok] == MISS).all()
+
+
 def test_device_resident_entry_points(teapot, oracle):
     import torch
     scene, g = teapot
