@@ -112,3 +112,22 @@ def test_empty_tree_and_empty_scene(oracle):
     want = ref.intersect(rays, CLS_TREE)
     got = oracle.intersect(Scene(nodes, lanes, bounds), rays, CLS_TREE)
     assert (want["prim"] == MISS).all() and got.tobytes() == want.tobytes()
+
+
+def test_reference_frame_loop_matches_golden_visibility():
+    """ref_trace_frame runs the reference's per-pixel order (closest chain, then canSeeLight from the record's OWN
+    hitPoint, main.cpp:182-219); its visibility must equal the fixture that was built from o + d*t hit points,
+    i.e. every shape class's hitPoint really is o + d*t bit for bit."""
+    z = np.load(os.path.join(GOLDEN, "teapot_frame.npz"))
+    w, h, step = int(z["width"]), int(z["height"]), int(z["step"])
+    ref = RefLib()
+    ref.add_reference_spheres(1, 16)
+    ref.add_reference_planes()
+    ref.add_reference_cylinder()
+    ref.add_mesh(os.path.join(GOLDEN, "teapot.dodm"))
+    ref.build_tree()
+    t, vis = ref.trace_frame(w, h, ALL, LIGHT0, 8)
+    sel = (np.arange(0, h, step)[:, None] * w + np.arange(0, w, step)[None, :]).ravel()
+    assert vis[sel].tobytes() == z["all_vis"].tobytes()
+    assert same_bits(t[sel], z["all_hits"]["t"]).all()
+    assert int(vis.sum()) == int(z["all_num_visible"])
