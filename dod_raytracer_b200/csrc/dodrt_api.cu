@@ -170,18 +170,12 @@ uint64_t frameSlots(const dodrt_frame *f)
 
 unsigned long long *nextCounter(dodrt_scene *s)
 {
-    return s->d_counters + (s->nextCounter.fetch_add(1) % kCounterSlots);
+    return s->d_counters + (size_t)(s->nextCounter.fetch_add(1) % kCounterSlots) * kCounterWords;
 }
 
-int ensureStream(dodrt_scene *s)
+int ensurePool(dodrt_scene *s)
 {
     std::lock_guard<std::mutex> lock(s->mutex);
-    if (!s->stream) {
-        CUDA_TRY(cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking));
-    }
-    if (!s->copyStream) {
-        CUDA_TRY(cudaStreamCreateWithFlags(&s->copyStream, cudaStreamNonBlocking));
-    }
     if (!s->pool) {
         cudaMemPoolProps props{};
         props.allocType = cudaMemAllocationTypePinned;
@@ -191,6 +185,20 @@ int ensureStream(dodrt_scene *s)
         CUDA_TRY(cudaMemPoolCreate(&s->pool, &props));
         uint64_t keep = UINT64_MAX;
         CUDA_TRY(cudaMemPoolSetAttribute(s->pool, cudaMemPoolAttrReleaseThreshold, &keep));
+    }
+    return DODRT_OK;
+}
+
+int ensureStream(dodrt_scene *s)
+{
+    int rc = ensurePool(s);
+    if (rc != DODRT_OK) return rc;
+    std::lock_guard<std::mutex> lock(s->mutex);
+    if (!s->stream) {
+        CUDA_TRY(cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking));
+    }
+    if (!s->copyStream) {
+        CUDA_TRY(cudaStreamCreateWithFlags(&s->copyStream, cudaStreamNonBlocking));
     }
     return DODRT_OK;
 }
@@ -229,7 +237,22 @@ int launchFrame(dodrt_scene *s, TraceMode mode, const dodrt_frame *frame, const 
     if (p.count == 0) {
         return DODRT_OK;
     }
-    CUDA_TRY(launch_trace(mode, p, s->cfg[p.variant][mode], stream));
+    // heavy-first tile order (see order_tiles_kernel): worth it when the kd-tree is in play and there are
+    // enough tiles to reorder
+    p.num_local_tiles = tiles;
+    p.tile_order = nullptr;
+    static const bool orderTiles = [] { const char *e = std::getenv("DODRT_TILE_ORDER"); return !e || std::atoi(e) != 0; }();
+    if (orderTiles && (frame->classes & DODRT_CLS_TREE) && s->dev.num_nodes != 0 && tiles >= 64) {
+        int rc = ensurePool(s);
+        if (rc != DODRT_OK) return rc;
+        CUDA_TRY(cudaMallocFromPoolAsync(&p.tile_order, sizeof(uint32_t) * tiles, s->pool, stream));
+    }
+    cudaError_t le = launch_trace(mode, p, s->cfg[p.variant][mode], stream);
+    if (p.tile_order) {
+        cudaFreeAsync(p.tile_order, stream);
+        s->launches.fetch_add(1);
+    }
+    if (le != cudaSuccess) return fail(DODRT_E_CUDA, "kernel launch failed: %s", cudaGetErrorString(le));
     s->launches.fetch_add(1);
     return DODRT_OK;
 }
@@ -269,7 +292,7 @@ int dodrt_scene_create(int device, dodrt_scene **scene)
         if (t) std::sscanf(t, "%u,%u,%u", &a, &b, &c);
         s->dev.tune[0] = a, s->dev.tune[1] = b, s->dev.tune[2] = c, s->dev.tune[3] = 0;
     }
-    cudaError_t e = cudaMalloc(&s->d_counters, sizeof(unsigned long long) * kCounterSlots);
+    cudaError_t e = cudaMalloc(&s->d_counters, sizeof(unsigned long long) * kCounterSlots * kCounterWords);
     s->variant = default_variant();
     for (int v = 0; v < kNumVariants; v++) {
         for (int m = 0; m < 3 && e == cudaSuccess; m++) {
@@ -455,6 +478,8 @@ int dodrt_intersect_device(dodrt_scene *s, const dodrt_ray *d_rays, uint64_t num
     p.hits = d_hits;
     p.counter = nextCounter(s);
     p.variant = s->variant;
+    p.tile_order = nullptr;
+    p.num_local_tiles = 0;
     CUDA_TRY(launch_trace(kModeRays, p, s->cfg[p.variant][kModeRays], static_cast<cudaStream_t>(stream)));
     s->launches.fetch_add(1);
     return DODRT_OK;

@@ -239,30 +239,29 @@ __device__ __forceinline__ void tree_enter(const DeviceScene &s, TreeState &st, 
     }
 }
 
-// Leaf phase with at most 16 rays waiting for triangles: the 32 lanes of the warp become 16 pairs, pair r
-// serves the r-th waiting ray, lane 2r tests slots 0..3 and lane 2r+1 slots 4..7 of that ray's current triangle
-// lane (ray and lane pointer travel by shuffle), and the owner merges the two answers in slot order: the
-// second half is accepted only if its t beats the clip left by the first half (strict <), which is exactly
-// the sequential result because each half already holds its own (t, id)-minimum below the incoming clip.
-__device__ __forceinline__ void leaf_step_shared(const DeviceScene &s, TreeState &st, unsigned leafMask, bool wantLeaf,
-                                                 const float o[3], const float d[3], bool any, float &clip, Hit &hit,
-                                                 bool &found, const uint32_t *stackNode, const float *stackTmin,
-                                                 const float *stackTmax)
+// Leaf phase for STRAGGLERS: at most 4 rays of the warp wait for triangles (the others are finished or at
+// nodes).  One ray per lane would leave >= 28 lanes idle, and a ray grazing the mesh visits >1000 triangle lanes
+// one after the other -- the critical path that kept single SMs busy long after the rest of the grid had
+// drained (profiles/r01_rank_tail.txt).  Here the warp splits into groups of G = 8/16/32 lanes, group g serves
+// the g-th waiting ray, and every lane tests ONE of the ray's next G triangle slots (ray by shuffle, 9 scalar
+// loads from the SoA lane).  The group's answer is the lexicographic minimum of (t, slot) over the accepted
+// slots, which is exactly what the reference's slot-by-slot loop with its strict `<` leaves behind
+// (triangle.cpp:119-139), so results stay bit-identical.
+__device__ __forceinline__ void leaf_step_coop(const DeviceScene &s, TreeState &st, unsigned leafMask, uint32_t nLeaf,
+                                               bool wantLeaf, const float o[3], const float d[3], bool any, float &clip,
+                                               Hit &hit, bool &found, const uint32_t *stackNode, const float *stackTmin,
+                                               const float *stackTmax)
 {
-    __shared__ uint8_t ownerOfRank[8][16]; // up to 8 warps per block
     const uint32_t lane = threadIdx.x & 31u;
-    uint8_t *table = ownerOfRank[(threadIdx.x >> 5) & 7u];
-    const uint32_t myRank = __popc(leafMask & ((1u << lane) - 1u));
-    if (wantLeaf) {
-        table[myRank] = (uint8_t)lane;
+    const uint32_t shift = nLeaf <= 1u ? 5u : (nLeaf <= 2u ? 4u : 3u);
+    const uint32_t G = 1u << shift;
+    const uint32_t g = lane >> shift, sub = lane & (G - 1u);
+    unsigned m = leafMask;
+    for (uint32_t i = 0; i < g; i++) {
+        m &= m - 1u; // drop the g lowest waiting lanes (g <= 3)
     }
-    __syncwarp();
-    const uint32_t nLeaf = __popc(leafMask);
-    const uint32_t unitRank = lane >> 1, half = lane & 1u;
-    const bool unitValid = unitRank < nLeaf;
-    const uint32_t owner = unitValid ? table[unitRank] : lane;
-    __syncwarp();
-    // ray of the owner
+    const bool groupValid = m != 0u;
+    const uint32_t owner = groupValid ? (uint32_t)__ffs((int)m) - 1u : lane;
     float ro[3], rd[3];
     ro[0] = __shfl_sync(0xffffffffu, o[0], owner);
     ro[1] = __shfl_sync(0xffffffffu, o[1], owner);
@@ -270,34 +269,42 @@ __device__ __forceinline__ void leaf_step_shared(const DeviceScene &s, TreeState
     rd[0] = __shfl_sync(0xffffffffu, d[0], owner);
     rd[1] = __shfl_sync(0xffffffffu, d[1], owner);
     rd[2] = __shfl_sync(0xffffffffu, d[2], owner);
-    float rclip = __shfl_sync(0xffffffffu, clip, owner);
-    const uint32_t rtri = __shfl_sync(0xffffffffu, st.triCur, owner);
-    Hit uh;
-    uh.t = 0.0f, uh.prim = DODRT_MISS, uh.u = uh.v = 0.0f;
-    bool uacc = false;
-    if (unitValid) {
-        const float4 *lanePtr = s.lanes4 + (size_t)(rtri >> 3) * 18;
-        uacc = lane_half_test(lanePtr, (int)half, rtri + 4u * half, ro, rd, rclip, uh);
+    const float rclip = __shfl_sync(0xffffffffu, clip, owner);
+    const uint32_t rcur = __shfl_sync(0xffffffffu, st.triCur, owner);
+    const uint32_t rend = __shfl_sync(0xffffffffu, st.triEnd, owner);
+    const uint32_t tri = rcur + sub;
+    bool acc = false;
+    float t = 0.0f, u = 0.0f, v = 0.0f;
+    if (groupValid && tri < rend) {
+        const float *base = reinterpret_cast<const float *>(s.lanes4) + (size_t)(tri >> 3) * 72 + (tri & 7u);
+        const float4 q0 = make_float4(__ldg(base), __ldg(base + 8), __ldg(base + 16), __ldg(base + 24));
+        const float4 q1 = make_float4(__ldg(base + 32), __ldg(base + 40), __ldg(base + 48), __ldg(base + 56));
+        const float4 q2 = make_float4(__ldg(base + 64), 0.0f, 0.0f, 0.0f);
+        acc = triangle_test_fast(q0, q1, q2, ro, rd, rclip, t, u, v);
     }
-    // owners collect the answers of their two units
-    const uint32_t src0 = wantLeaf ? 2u * myRank : lane, src1 = wantLeaf ? 2u * myRank + 1u : lane;
-    const unsigned accMask = __ballot_sync(0xffffffffu, uacc);
-    const float t0 = __shfl_sync(0xffffffffu, uh.t, src0), t1 = __shfl_sync(0xffffffffu, uh.t, src1);
-    const float u0 = __shfl_sync(0xffffffffu, uh.u, src0), u1 = __shfl_sync(0xffffffffu, uh.u, src1);
-    const float v0 = __shfl_sync(0xffffffffu, uh.v, src0), v1 = __shfl_sync(0xffffffffu, uh.v, src1);
-    const uint32_t p0 = __shfl_sync(0xffffffffu, uh.prim, src0), p1 = __shfl_sync(0xffffffffu, uh.prim, src1);
+    float best = acc ? t : kInfinity; // accepted t are finite and positive, so min() is exact
+    for (uint32_t off = G >> 1; off != 0u; off >>= 1) {
+        best = fminf(best, __shfl_xor_sync(0xffffffffu, best, off)); // xor < G stays inside the group
+    }
+    const unsigned winners = __ballot_sync(0xffffffffu, acc && t == best);
+    // owners pick up their group's answer: lowest winning lane = lowest slot id
+    const uint32_t myGroup = __popc(leafMask & ((1u << lane) - 1u));
+    const unsigned groupLanes = (G == 32u ? 0xffffffffu : ((1u << G) - 1u)) << ((myGroup << shift) & 31u);
+    const unsigned mine = wantLeaf ? (winners & groupLanes) : 0u;
+    const uint32_t src = mine ? (uint32_t)__ffs((int)mine) - 1u : lane;
+    const float wt = __shfl_sync(0xffffffffu, t, src);
+    const float wu = __shfl_sync(0xffffffffu, u, src);
+    const float wv = __shfl_sync(0xffffffffu, v, src);
     if (wantLeaf) {
-        if ((accMask >> src0) & 1u) {
-            clip = t0;
-            hit.t = t0, hit.prim = p0, hit.u = u0, hit.v = v0;
+        if (mine) {
+            clip = wt;
+            hit.t = wt;
+            hit.prim = (DODRT_KIND_TRIANGLE << DODRT_KIND_SHIFT) | (st.triCur + (src & (G - 1u)));
+            hit.u = wu;
+            hit.v = wv;
             found = true;
         }
-        if (((accMask >> src1) & 1u) && t1 < clip) {
-            clip = t1;
-            hit.t = t1, hit.prim = p1, hit.u = u1, hit.v = v1;
-            found = true;
-        }
-        st.triCur += kLane;
+        st.triCur = st.triCur + G < st.triEnd ? st.triCur + G : st.triEnd;
         if (any && found) {
             st.live = false; // kdtree.cpp:338-341
         } else if (st.triCur == st.triEnd) {
@@ -328,8 +335,9 @@ __device__ __forceinline__ bool kdtree_query_voted(const DeviceScene &s, bool en
         const uint32_t nLeaf = __popc(leafMask), nNode = __popc(nodeMask);
         if (nNode == 0u || (nLeaf != 0u && (nLeaf * s.tune[1] >= nNode * s.tune[0] || nodeRun >= s.tune[2]))) {
             nodeRun = 0;
-            if (SHARE && nLeaf <= 16u) {
-                leaf_step_shared(s, st, leafMask, wantLeaf, o, d, any, clip, hit, found, stackNode, stackTmin, stackTmax);
+            if (SHARE && nLeaf <= 4u) {
+                leaf_step_coop(s, st, leafMask, nLeaf, wantLeaf, o, d, any, clip, hit, found, stackNode, stackTmin,
+                               stackTmax);
             } else if (wantLeaf) {
                 leaf_step<SOA>(s, st, o, d, any, clip, hit, found, stackNode, stackTmin, stackTmax);
             }
@@ -404,14 +412,20 @@ __device__ __forceinline__ bool query(const DeviceScene &s, uint32_t classes, bo
     return found;
 }
 
-// slot -> pixel for the frame modes (see dodrt_frame in include/dodrt.h): tiles round-robin over
-// ranks, 8x4 pixel blocks inside a tile so that one warp = one block.
-__device__ __forceinline__ bool slot_to_pixel(const dodrt_frame &f, uint32_t tiles_x, uint64_t slot, uint32_t &col,
-                                              uint32_t &row)
+// work item -> pixel for the frame modes (see dodrt_frame in include/dodrt.h): tiles round-robin over
+// ranks, 8x4 pixel blocks inside a tile so that one warp = one block.  `order` (optional) is the order in which
+// the call's local tiles are PROCESSED; `slot` is where the item's result goes in a compact buffer and does
+// not depend on it.
+__device__ __forceinline__ bool slot_to_pixel(const dodrt_frame &f, uint32_t tiles_x, const uint32_t *order, uint64_t item,
+                                              uint32_t &col, uint32_t &row, uint64_t &slot)
 {
     const uint32_t tilePixels = f.tile_w * f.tile_h;
-    const uint32_t localTile = (uint32_t)(slot / tilePixels);
-    const uint32_t in = (uint32_t)(slot % tilePixels);
+    uint32_t localTile = (uint32_t)(item / tilePixels);
+    const uint32_t in = (uint32_t)(item % tilePixels);
+    if (order) {
+        localTile = __ldg(order + localTile);
+    }
+    slot = (uint64_t)localTile * tilePixels + in;
     const uint32_t tile = f.first_tile + localTile * f.tile_stride;
     const uint32_t tx = tile % tiles_x, ty = tile / tiles_x;
     const uint32_t block = in >> 5, lane = in & 31u;
@@ -420,6 +434,57 @@ __device__ __forceinline__ bool slot_to_pixel(const dodrt_frame &f, uint32_t til
     col = tx * f.tile_w + bx * 8 + (lane & 7u);
     row = ty * f.tile_h + by * 4 + (lane >> 3);
     return col < f.width && row < f.height;
+}
+
+// Heavy-first tile order.  A persistent kernel ends when its slowest warp ends, and a 32-ray batch that grazes
+// the mesh runs for hundreds of microseconds; started in natural (top-to-bottom) order such batches begin
+// half-way through the kernel and the other SMs idle while they finish (profiles/r01_rank_tail.txt).  One thread
+// per local tile samples 4x4 of the tile's rays (the primary ray, or the pixel's shadow ray built from its
+// primary hit) against the kd-tree bounds; tiles with a ray entering the bounds are queued from the front,
+// the others from the back.  Only the processing order changes -- never a result.
+template <int MODE> __global__ void order_tiles_kernel(const TraceParams p)
+{
+    const uint32_t local = blockIdx.x * blockDim.x + threadIdx.x;
+    if (local >= p.num_local_tiles) {
+        return;
+    }
+    const dodrt_frame &f = p.frame;
+    const uint32_t tile = f.first_tile + local * f.tile_stride;
+    const uint32_t tx = tile % p.tiles_x, ty = tile / p.tiles_x;
+    const float o[3] = {f.origin[0], f.origin[1], f.origin[2]};
+    bool heavy = false;
+    for (uint32_t sy = 0; sy < 4 && !heavy; sy++) {
+        for (uint32_t sx = 0; sx < 4 && !heavy; sx++) {
+            const uint32_t ix = (2 * sx + 1) * f.tile_w / 8, iy = (2 * sy + 1) * f.tile_h / 8;
+            const uint32_t col = tx * f.tile_w + ix, row = ty * f.tile_h + iy;
+            if (col >= f.width || row >= f.height) {
+                continue;
+            }
+            float ro[3] = {o[0], o[1], o[2]}, rd[3];
+            float clip = kInfinity;
+            primary_dir(__ldg(p.xs + col), __ldg(p.ys + row), rd);
+            if (MODE == kModeShadow) {
+                const uint32_t in = ((iy >> 2) * (f.tile_w >> 3) + (ix >> 3)) * 32u + (iy & 3u) * 8u + (ix & 7u);
+                const uint64_t idx = f.compact ? (uint64_t)local * f.tile_w * f.tile_h + in : (uint64_t)row * f.width + col;
+                const float4 ph = reinterpret_cast<const float4 *>(p.hits)[idx];
+                if (__float_as_uint(ph.y) == DODRT_MISS) {
+                    continue;
+                }
+                float so[3], sd[3];
+                shadow_ray(o, rd, ph.x, p.light, so, sd, clip);
+                ro[0] = so[0], ro[1] = so[1], ro[2] = so[2];
+                rd[0] = sd[0], rd[1] = sd[1], rd[2] = sd[2];
+            }
+            const float inv[3] = {1.0f / rd[0], 1.0f / rd[1], 1.0f / rd[2]};
+            float tmin, tmax;
+            heavy = slab(p.scene.bmin, p.scene.bmax, ro, inv, clip, tmin, tmax) && !(tmin > clip);
+        }
+    }
+    if (heavy) {
+        p.tile_order[atomicAdd(p.counter + 1, 1ull)] = local;
+    } else {
+        p.tile_order[p.num_local_tiles - 1u - (uint32_t)atomicAdd(p.counter + 2, 1ull)] = local;
+    }
 }
 
 #ifndef DODRT_MINBLOCKS
@@ -463,8 +528,9 @@ template <int MODE, int VARIANT> __global__ void __launch_bounds__(128, DODRT_MI
             }
         } else {
             uint32_t col = 0, row = 0;
-            const bool inside = inRange && slot_to_pixel(p.frame, p.tiles_x, item, col, row);
-            const uint64_t out = p.frame.compact ? item : (uint64_t)row * p.frame.width + col;
+            uint64_t slot = 0;
+            const bool inside = inRange && slot_to_pixel(p.frame, p.tiles_x, p.tile_order, item, col, row, slot);
+            const uint64_t out = p.frame.compact ? slot : (uint64_t)row * p.frame.width + col;
             const float o[3] = {p.frame.origin[0], p.frame.origin[1], p.frame.origin[2]};
             float d[3] = {0.0f, 0.0f, 1.0f};
             if (inside) {
@@ -621,8 +687,16 @@ cudaError_t trace_launch_config(int device, TraceMode mode, int variant, LaunchC
 
 cudaError_t launch_trace(TraceMode mode, const TraceParams &p, const LaunchConfig &cfg, cudaStream_t stream)
 {
-    cudaError_t e = cudaMemsetAsync(p.counter, 0, sizeof(unsigned long long), stream);
+    cudaError_t e = cudaMemsetAsync(p.counter, 0, sizeof(unsigned long long) * kCounterWords, stream);
     if (e != cudaSuccess) return e;
+    if (p.tile_order && mode != kModeRays) {
+        const unsigned blocks = (p.num_local_tiles + 127u) / 128u;
+        if (mode == kModePrimary) {
+            order_tiles_kernel<kModePrimary><<<blocks, 128, 0, stream>>>(p);
+        } else {
+            order_tiles_kernel<kModeShadow><<<blocks, 128, 0, stream>>>(p);
+        }
+    }
     switch (p.variant) {
     case 0: launch_mode<0>(mode, p, cfg, stream); break;
     case 1: launch_mode<1>(mode, p, cfg, stream); break;

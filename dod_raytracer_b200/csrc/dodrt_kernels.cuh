@@ -30,9 +30,16 @@ struct TraceParams {
     const float *xs, *ys;
     float light[3];
     uint8_t *visible;
-    // dynamic work distribution: one counter per launch, zeroed on the stream before the launch
+    // dynamic work distribution: kCounterWords counters per launch, zeroed on the stream before the launch:
+    // [0] next work item, [1] heavy tiles placed so far, [2] light tiles placed so far
     unsigned long long *counter;
+    // frame modes: optional processing order of the call's local tiles (heavy-first, see order_tiles_kernel);
+    // results still land in the natural slots.  nullptr = natural order.
+    uint32_t *tile_order;
+    uint32_t num_local_tiles;
 };
+
+constexpr int kCounterWords = 4;
 
 struct LaunchConfig {
     int grid;

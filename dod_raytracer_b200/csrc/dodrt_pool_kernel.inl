@@ -122,8 +122,9 @@ template <int MODE> __global__ void __launch_bounds__(32 * kWarpsPerBlock) trace
                 }
             } else {
                 uint32_t col = 0, row = 0;
-                const bool inside = inRange && slot_to_pixel(p.frame, p.tiles_x, item, col, row);
-                slot = p.frame.compact ? item : (uint64_t)row * p.frame.width + col;
+                uint64_t compactSlot = 0;
+                const bool inside = inRange && slot_to_pixel(p.frame, p.tiles_x, p.tile_order, item, col, row, compactSlot);
+                slot = p.frame.compact ? compactSlot : (uint64_t)row * p.frame.width + col;
                 writes = inside || (inRange && p.frame.compact);
                 r.o[0] = p.frame.origin[0], r.o[1] = p.frame.origin[1], r.o[2] = p.frame.origin[2];
                 if (inside) {
