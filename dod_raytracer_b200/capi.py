@@ -32,7 +32,7 @@ EXPORTED_SYMBOLS = [
     "dodrt_abi_version", "dodrt_last_error", "dodrt_device_count",
     "dodrt_scene_create", "dodrt_scene_destroy", "dodrt_scene_set_kdtree", "dodrt_scene_set_spheres",
     "dodrt_scene_set_planes", "dodrt_scene_set_cylinders", "dodrt_scene_set_boxes", "dodrt_scene_set_epsilon",
-    "dodrt_scene_set_kernel_variant",
+    "dodrt_scene_set_kernel_variant", "dodrt_scene_set_shading", "dodrt_render",
     "dodrt_intersect", "dodrt_trace_primary", "dodrt_trace_shadow", "dodrt_trace_frame",
     "dodrt_intersect_device", "dodrt_trace_primary_device", "dodrt_trace_shadow_device",
     "dodrt_frame_assemble_device", "dodrt_frame_local_pixels", "dodrt_frame_pixel_map", "dodrt_scene_launch_count",
@@ -176,6 +176,25 @@ class Scene:
     def set_cylinders(self, cylinders: np.ndarray):
         cyl = np.ascontiguousarray(cylinders, CYL_DT)
         _check(self._lib.dodrt_scene_set_cylinders(self._h, _ptr(cyl), C.c_uint32(len(cyl))))
+
+    def set_shading(self, tri_attributes: np.ndarray, mesh_colors: np.ndarray, sphere_colors: np.ndarray,
+                    plane_colors: np.ndarray):
+        """tri_attributes: the reference's Triangle::Attributes lanes (320 B each) as uint32 [lanes, 80]."""
+        attrs = np.ascontiguousarray(tri_attributes, np.uint32).reshape(-1, 80)
+        mc = np.ascontiguousarray(mesh_colors, np.float32).reshape(-1, 3)
+        sc = np.ascontiguousarray(sphere_colors, np.float32).reshape(-1, 3)
+        pc = np.ascontiguousarray(plane_colors, np.float32).reshape(-1, 3)
+        _check(self._lib.dodrt_scene_set_shading(self._h, _ptr(attrs), C.c_uint32(len(attrs)), _ptr(mc),
+                                                 C.c_uint32(len(mc)), _ptr(sc), _ptr(pc)))
+
+    def render(self, frame: Frame, xs, ys, lights, depth: int = 10, out: Optional[np.ndarray] = None) -> np.ndarray:
+        """dodrt_render: the reference's rayTrace for the whole frame; lights = [[x, y, z, intensity], ...]."""
+        xs, ys = np.ascontiguousarray(xs, np.float32), np.ascontiguousarray(ys, np.float32)
+        lights = np.ascontiguousarray(lights, np.float32).reshape(-1, 4)
+        rgb = out if out is not None else np.empty((frame.height, frame.width, 3), np.uint8)
+        _check(self._lib.dodrt_render(self._h, C.byref(frame), _ptr(xs), _ptr(ys), _ptr(lights), C.c_uint32(len(lights)),
+                                      C.c_uint32(depth), _ptr(rgb)))
+        return rgb
 
     def set_kernel_variant(self, variant: int):
         _check(self._lib.dodrt_scene_set_kernel_variant(self._h, C.c_int(variant)))

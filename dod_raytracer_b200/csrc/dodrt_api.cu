@@ -82,10 +82,12 @@ struct dodrt_scene {
     float *d_planes = nullptr;
     dodrt_cylinder *d_cylinders = nullptr;
     float *d_boxes = nullptr;
+    uint32_t *d_triAttrs = nullptr;
+    float *d_meshColors = nullptr, *d_sphereColors = nullptr, *d_planeColors = nullptr;
     unsigned long long *d_counters = nullptr;
     std::atomic<uint32_t> nextCounter{0};
     std::atomic<uint64_t> launches{0};
-    LaunchConfig cfg[kNumVariants][3]{};
+    LaunchConfig cfg[kNumVariants][kNumModes]{};
     int variant = kDefaultVariant;
     uint32_t treeDepth = 0;
     std::mutex mutex; // guards scene mutation and the lazily created staging stream
@@ -295,7 +297,7 @@ int dodrt_scene_create(int device, dodrt_scene **scene)
     cudaError_t e = cudaMalloc(&s->d_counters, sizeof(unsigned long long) * kCounterSlots * kCounterWords);
     s->variant = default_variant();
     for (int v = 0; v < kNumVariants; v++) {
-        for (int m = 0; m < 3 && e == cudaSuccess; m++) {
+        for (int m = 0; m < kNumModes && e == cudaSuccess; m++) {
             e = trace_launch_config(device, (TraceMode)m, v, &s->cfg[v][m]);
         }
     }
@@ -323,6 +325,10 @@ int dodrt_scene_destroy(dodrt_scene *s)
     freeDevice(s->d_planes);
     freeDevice(s->d_cylinders);
     freeDevice(s->d_boxes);
+    freeDevice(s->d_triAttrs);
+    freeDevice(s->d_meshColors);
+    freeDevice(s->d_sphereColors);
+    freeDevice(s->d_planeColors);
     freeDevice(s->d_counters);
     delete s;
     return DODRT_OK;
@@ -440,6 +446,51 @@ int dodrt_scene_set_cylinders(dodrt_scene *s, const dodrt_cylinder *cylinders, u
     }
     s->dev.cylinders = s->d_cylinders;
     s->dev.num_cylinders = num_cylinders;
+    return DODRT_OK;
+}
+
+int dodrt_scene_set_shading(dodrt_scene *s, const void *tri_attributes, uint32_t num_tri_lanes, const float *mesh_colors,
+                            uint32_t num_meshes, const float *sphere_colors, const float *plane_colors)
+{
+    if (!s) return fail(DODRT_E_INVALID, "scene is NULL");
+    if (num_tri_lanes != s->dev.num_tri_lanes) {
+        return fail(DODRT_E_INVALID, "attributes for %u lanes but the kd-tree has %u", num_tri_lanes, s->dev.num_tri_lanes);
+    }
+    if (num_tri_lanes && (!tri_attributes || !mesh_colors || !num_meshes)) return fail(DODRT_E_INVALID, "NULL attributes");
+    if ((s->dev.num_spheres && !sphere_colors) || (s->dev.num_planes && !plane_colors)) {
+        return fail(DODRT_E_INVALID, "NULL sphere/plane colours");
+    }
+    if (num_tri_lanes) { // every meshAttrIdx must address a mesh colour
+        const uint32_t *a = static_cast<const uint32_t *>(tri_attributes);
+        for (uint32_t lane = 0; lane < num_tri_lanes; lane++) {
+            for (int j = 0; j < kLane; j++) {
+                if (a[(size_t)lane * 80 + j] >= num_meshes) {
+                    return fail(DODRT_E_INVALID, "meshAttrIdx %u of lane %u out of range (%u meshes)",
+                                a[(size_t)lane * 80 + j], lane, num_meshes);
+                }
+            }
+        }
+    }
+    std::lock_guard<std::mutex> lock(s->mutex);
+    DeviceGuard guard(s->device);
+    if (!guard.ok) return fail(DODRT_E_CUDA, "cannot select device %d", s->device);
+    freeDevice(s->d_triAttrs);
+    freeDevice(s->d_meshColors);
+    freeDevice(s->d_sphereColors);
+    freeDevice(s->d_planeColors);
+    auto upload = [&](auto **dst, const void *src, size_t bytes) -> cudaError_t {
+        if (!bytes) return cudaSuccess;
+        cudaError_t e = cudaMalloc(dst, bytes);
+        return e == cudaSuccess ? cudaMemcpy(*dst, src, bytes, cudaMemcpyHostToDevice) : e;
+    };
+    CUDA_TRY(upload(&s->d_triAttrs, tri_attributes, (size_t)num_tri_lanes * 320));
+    CUDA_TRY(upload(&s->d_meshColors, mesh_colors, (size_t)num_meshes * 12));
+    CUDA_TRY(upload(&s->d_sphereColors, sphere_colors, (size_t)s->dev.num_spheres * 12));
+    CUDA_TRY(upload(&s->d_planeColors, plane_colors, (size_t)s->dev.num_planes * 12));
+    s->dev.tri_attrs = s->d_triAttrs;
+    s->dev.mesh_colors = s->d_meshColors;
+    s->dev.sphere_colors = s->d_sphereColors;
+    s->dev.plane_colors = s->d_planeColors;
     return DODRT_OK;
 }
 
@@ -715,6 +766,86 @@ int dodrt_trace_shadow(dodrt_scene *s, const dodrt_frame *frame, const float *xs
     if (rc != DODRT_OK) return rc;
     if (e == cudaSuccess) e = es;
     if (e != cudaSuccess) return fail(DODRT_E_CUDA, "dodrt_trace_shadow: %s", cudaGetErrorString(e));
+    return DODRT_OK;
+}
+
+// ---- shading + bounce loop ----------------------------------------------------------------
+
+int dodrt_render(dodrt_scene *s, const dodrt_frame *frame, const float *xs, const float *ys, const float *lights,
+                 uint32_t num_lights, uint32_t depth, uint8_t *rgb)
+{
+    if (!s) return fail(DODRT_E_INVALID, "scene is NULL");
+    int rc = checkFrame(frame);
+    if (rc != DODRT_OK) return rc;
+    if (!xs || !ys || !rgb || (num_lights && !lights)) return fail(DODRT_E_INVALID, "NULL argument");
+    if (num_lights > (uint32_t)kMaxLights) return fail(DODRT_E_LIMIT, "%u lights exceed the limit of %d", num_lights, kMaxLights);
+    if ((s->dev.num_tri_lanes && !s->dev.tri_attrs) || (s->dev.num_spheres && !s->dev.sphere_colors) ||
+        (s->dev.num_planes && !s->dev.plane_colors)) {
+        return fail(DODRT_E_INVALID, "dodrt_scene_set_shading has not been called for this scene");
+    }
+    rc = ensureStream(s);
+    if (rc != DODRT_OK) return rc;
+    DeviceGuard guard(s->device);
+    if (!guard.ok) return fail(DODRT_E_CUDA, "cannot select device %d", s->device);
+    cudaStream_t st = s->stream;
+    const uint64_t n = (uint64_t)frame->width * frame->height;
+    float *d_tables = nullptr;
+    RenderParams rp{};
+    rp.scene = s->dev;
+    rp.width = frame->width;
+    rp.height = frame->height;
+    for (int k = 0; k < 3; k++) rp.origin[k] = frame->origin[k];
+    rp.num_lights = num_lights;
+    for (uint32_t l = 0; l < num_lights; l++) {
+        for (int k = 0; k < 4; k++) rp.lights[l][k] = lights[l * 4 + k];
+    }
+    cudaError_t e = cudaMallocFromPoolAsync(&d_tables, ((size_t)frame->width + frame->height) * sizeof(float), s->pool, st);
+    if (e == cudaSuccess) e = cudaMallocFromPoolAsync(&rp.rays, n * sizeof(dodrt_ray), s->pool, st);
+    if (e == cudaSuccess) e = cudaMallocFromPoolAsync(&rp.hits, n * sizeof(dodrt_hit), s->pool, st);
+    if (e == cudaSuccess) e = cudaMallocFromPoolAsync(&rp.visible, n * (num_lights ? num_lights : 1), s->pool, st);
+    if (e == cudaSuccess) e = cudaMallocFromPoolAsync(&rp.accum, n * sizeof(float4), s->pool, st);
+    if (e == cudaSuccess) e = cudaMallocFromPoolAsync(&rp.rgb, n * 3, s->pool, st);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(d_tables, xs, frame->width * sizeof(float), cudaMemcpyHostToDevice, st);
+    if (e == cudaSuccess) {
+        e = cudaMemcpyAsync(d_tables + frame->width, ys, frame->height * sizeof(float), cudaMemcpyHostToDevice, st);
+    }
+    rp.xs = d_tables;
+    rp.ys = d_tables ? d_tables + frame->width : nullptr;
+    if (e == cudaSuccess) e = launch_render_init(rp, st);
+    if (e == cudaSuccess) s->launches.fetch_add(1);
+    for (uint32_t k = 0; k < depth && e == cudaSuccess; k++) { // main.cpp:312
+        TraceParams p{};
+        p.scene = s->dev;
+        p.classes = frame->classes;
+        p.rays = rp.rays;
+        p.count = n;
+        p.hits = rp.hits;
+        p.variant = s->variant;
+        p.counter = nextCounter(s);
+        e = launch_trace(kModeRays, p, s->cfg[p.variant][kModeRays], st); // closest-hit chain, main.cpp:314-321
+        if (e == cudaSuccess) s->launches.fetch_add(1);
+        for (uint32_t l = 0; l < num_lights && e == cudaSuccess; l++) { // canSeeLight per light, main.cpp:226
+            p.counter = nextCounter(s);
+            p.visible = rp.visible + n * l;
+            for (int c = 0; c < 3; c++) p.light[c] = rp.lights[l][c];
+            e = launch_trace(kModeShadowRays, p, s->cfg[p.variant][kModeShadowRays], st);
+            if (e == cudaSuccess) s->launches.fetch_add(1);
+        }
+        if (e == cudaSuccess) e = launch_render_shade(rp, k, st);
+        if (e == cudaSuccess) s->launches.fetch_add(1);
+    }
+    if (e == cudaSuccess) e = launch_render_finish(rp, st);
+    if (e == cudaSuccess) s->launches.fetch_add(1);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(rgb, rp.rgb, n * 3, cudaMemcpyDeviceToHost, st);
+    if (d_tables) cudaFreeAsync(d_tables, st);
+    if (rp.rays) cudaFreeAsync(rp.rays, st);
+    if (rp.hits) cudaFreeAsync(rp.hits, st);
+    if (rp.visible) cudaFreeAsync(rp.visible, st);
+    if (rp.accum) cudaFreeAsync(rp.accum, st);
+    if (rp.rgb) cudaFreeAsync(rp.rgb, st);
+    cudaError_t es = cudaStreamSynchronize(st);
+    if (e == cudaSuccess) e = es;
+    if (e != cudaSuccess) return fail(DODRT_E_CUDA, "dodrt_render: %s", cudaGetErrorString(e));
     return DODRT_OK;
 }
 

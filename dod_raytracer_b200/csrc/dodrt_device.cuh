@@ -42,6 +42,12 @@ struct DeviceScene {
     const float *box_lanes;    // minx miny minz maxx maxy maxz [8]
     uint32_t num_boxes;
     float epsilon;
+    // shading attributes (only read by the render kernels): Triangle::m_triangleAttributes in the reference's
+    // layout (80 words per lane, triangle.h:45-51), one colour per mesh / sphere / plane
+    const uint32_t *tri_attrs;
+    const float *mesh_colors;
+    const float *sphere_colors;
+    const float *plane_colors;
     // traversal scheduling knobs (dodrt_kernels.cu): leaf phase runs when nLeaf*tune[1] >= nNode*tune[0], or after
     // tune[2] consecutive node phases
     uint32_t tune[4];

@@ -504,10 +504,30 @@ template <int MODE, int VARIANT> __global__ void __launch_bounds__(128, DODRT_MI
         }
         const uint64_t item = base + lane;
         const bool inRange = item < p.count;
-        if (MODE == kModeRays) {
+        if (MODE == kModeShadowRays) {
+            // canSeeLight (main.cpp:182-219) for an explicit ray batch: shadow ray from rays[i]'s hit point
+            // (hits[i]) to p.light; visible[i] = 1 iff there was a hit and nothing blocks the light
+            float so[3] = {0.0f, 0.0f, 0.0f}, sd[3] = {0.0f, 0.0f, 1.0f}, sclip = 0.0f;
+            bool cast = false;
+            if (inRange) {
+                const float4 *src = reinterpret_cast<const float4 *>(p.rays + item);
+                const float4 a = src[0], b = src[1];
+                const float4 ph = reinterpret_cast<const float4 *>(p.hits)[item];
+                if (!(__float_as_uint(b.w) & DODRT_RAY_SKIP) && __float_as_uint(ph.y) != DODRT_MISS) {
+                    const float o[3] = {a.x, a.y, a.z}, d[3] = {a.w, b.x, b.y};
+                    shadow_ray(o, d, ph.x, p.light, so, sd, sclip);
+                    cast = true;
+                }
+            }
+            Hit h;
+            const bool blocked = query<VARIANT>(p.scene, p.classes, cast, so, sd, true, sclip, h);
+            if (inRange) {
+                p.visible[item] = (cast && !blocked) ? 1 : 0;
+            }
+        } else if (MODE == kModeRays) {
             float o[3] = {0.0f, 0.0f, 0.0f}, d[3] = {0.0f, 0.0f, 1.0f};
             float clip = 0.0f;
-            bool any = false;
+            bool any = false, skip = false;
             if (inRange) {
                 const float4 *src = reinterpret_cast<const float4 *>(p.rays + item);
                 const float4 a = __ldg(src), b = __ldg(src + 1);
@@ -515,9 +535,10 @@ template <int MODE, int VARIANT> __global__ void __launch_bounds__(128, DODRT_MI
                 d[0] = a.w, d[1] = b.x, d[2] = b.y;
                 clip = b.z;
                 any = (__float_as_uint(b.w) & DODRT_RAY_ANY) != 0u;
+                skip = (__float_as_uint(b.w) & DODRT_RAY_SKIP) != 0u;
             }
             Hit h;
-            const bool found = query<VARIANT>(p.scene, p.classes, inRange, o, d, any, clip, h);
+            const bool found = query<VARIANT>(p.scene, p.classes, inRange && !skip, o, d, any, clip, h);
             if (inRange) {
                 if (any) { // any-hit defines only hit/miss
                     h.t = clip;
@@ -622,8 +643,10 @@ template <int MODE, int VARIANT> cudaError_t config_for(int device, LaunchConfig
     int sms = 0, perSm = 0;
     cudaError_t e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
     if (e != cudaSuccess) return e;
-    if constexpr (VARIANT == 4) {
+    if constexpr (VARIANT == 4 && MODE != kModeShadowRays) {
         e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, trace_kernel_pool<MODE>, 128, 0);
+    } else if constexpr (VARIANT == 4) { // the pool kernel has no explicit-ray shadow mode: variant 3 serves it
+        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, trace_kernel<MODE, 3>, 128, 0);
     } else {
         e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, trace_kernel<MODE, VARIANT>, 128, 0);
     }
@@ -636,8 +659,10 @@ template <int MODE, int VARIANT> cudaError_t config_for(int device, LaunchConfig
 
 template <int MODE, int VARIANT> void launch_one(const TraceParams &p, const LaunchConfig &cfg, cudaStream_t stream)
 {
-    if constexpr (VARIANT == 4) {
+    if constexpr (VARIANT == 4 && MODE != kModeShadowRays) {
         trace_kernel_pool<MODE><<<cfg.grid, cfg.block, 0, stream>>>(p);
+    } else if constexpr (VARIANT == 4) {
+        trace_kernel<MODE, 3><<<cfg.grid, cfg.block, 0, stream>>>(p);
     } else {
         trace_kernel<MODE, VARIANT><<<cfg.grid, cfg.block, 0, stream>>>(p);
     }
@@ -648,7 +673,8 @@ template <int VARIANT> cudaError_t config_mode(int device, TraceMode mode, Launc
     switch (mode) {
     case kModeRays: return config_for<kModeRays, VARIANT>(device, cfg);
     case kModePrimary: return config_for<kModePrimary, VARIANT>(device, cfg);
-    default: return config_for<kModeShadow, VARIANT>(device, cfg);
+    case kModeShadow: return config_for<kModeShadow, VARIANT>(device, cfg);
+    default: return config_for<kModeShadowRays, VARIANT>(device, cfg);
     }
 }
 
@@ -657,7 +683,8 @@ template <int VARIANT> void launch_mode(TraceMode mode, const TraceParams &p, co
     switch (mode) {
     case kModeRays: launch_one<kModeRays, VARIANT>(p, cfg, stream); break;
     case kModePrimary: launch_one<kModePrimary, VARIANT>(p, cfg, stream); break;
-    default: launch_one<kModeShadow, VARIANT>(p, cfg, stream); break;
+    case kModeShadow: launch_one<kModeShadow, VARIANT>(p, cfg, stream); break;
+    default: launch_one<kModeShadowRays, VARIANT>(p, cfg, stream); break;
     }
 }
 
@@ -689,7 +716,7 @@ cudaError_t launch_trace(TraceMode mode, const TraceParams &p, const LaunchConfi
 {
     cudaError_t e = cudaMemsetAsync(p.counter, 0, sizeof(unsigned long long) * kCounterWords, stream);
     if (e != cudaSuccess) return e;
-    if (p.tile_order && mode != kModeRays) {
+    if (p.tile_order && (mode == kModePrimary || mode == kModeShadow)) {
         const unsigned blocks = (p.num_local_tiles + 127u) / 128u;
         if (mode == kModePrimary) {
             order_tiles_kernel<kModePrimary><<<blocks, 128, 0, stream>>>(p);

@@ -8,7 +8,9 @@ enum TraceMode : int {
     kModeRays = 0,    // explicit dodrt_ray batch            (dodrt_intersect*)
     kModePrimary = 1, // in-kernel primary ray generation     (dodrt_trace_primary*)
     kModeShadow = 2,  // in-kernel shadow ray generation      (dodrt_trace_shadow*)
+    kModeShadowRays = 3, // shadow rays from an explicit ray batch + its hits (bounce loop of dodrt_render*)
 };
+constexpr int kNumModes = 4;
 
 constexpr int kNumVariants = 6;    // see the header comment of dodrt_kernels.cu
 constexpr int kDefaultVariant = 3;
@@ -49,6 +51,25 @@ struct LaunchConfig {
 // Occupancy-derived persistent launch shape for the given device (cached by the caller).
 cudaError_t trace_launch_config(int device, TraceMode mode, int variant, LaunchConfig *cfg);
 cudaError_t launch_trace(TraceMode mode, const TraceParams &p, const LaunchConfig &cfg, cudaStream_t stream);
+
+// ---- shading / bounce loop (dodrt_render_kernels.cu): rayTrace, main.cpp:273-347 ---------------------------------
+constexpr int kMaxLights = 16;
+struct RenderParams {
+    DeviceScene scene;
+    uint32_t width, height;
+    float origin[3];
+    const float *xs, *ys;
+    dodrt_ray *rays;     // current ray of every pixel
+    dodrt_hit *hits;     // its closest hit
+    uint8_t *visible;    // [num_lights][pixels] canSeeLight results of this bounce
+    float4 *accum;       // finalColor
+    uint8_t *rgb;        // output, 3 bytes per pixel
+    uint32_t num_lights;
+    float lights[kMaxLights][4]; // position xyz, intensity (light.h:4-8)
+};
+cudaError_t launch_render_init(const RenderParams &p, cudaStream_t stream);
+cudaError_t launch_render_shade(const RenderParams &p, uint32_t bounce, cudaStream_t stream);
+cudaError_t launch_render_finish(const RenderParams &p, cudaStream_t stream);
 
 // Multi-GPU: gathered per-rank compact results -> row-major frame (one thread per pixel).
 cudaError_t launch_assemble(const dodrt_frame &frame, uint32_t tiles_x, const dodrt_hit *compactHits,

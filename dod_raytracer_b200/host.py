@@ -42,8 +42,9 @@ def load() -> C.CDLL:
         lib = C.CDLL(LIB_PATH)
         lib.dodrt_host_last_error.restype = C.c_char_p
         lib.dodrt_host_epsilon.restype = C.c_float
+        lib.dodrt_host_num_meshes.restype = C.c_uint32
         for name in ("nodes", "tri_lanes", "prim_nums", "bounds", "tri_normals", "sphere_lanes", "sphere_colors",
-                     "plane_lanes", "plane_colors", "cylinders", "box_lanes"):
+                     "plane_lanes", "plane_colors", "cylinders", "box_lanes", "tri_attributes", "mesh_colors"):
             getattr(lib, f"dodrt_host_{name}").restype = C.c_void_p
         lib.dodrt_host_add_cylinder.argtypes = [C.c_void_p, C.c_float, C.c_float, C.c_void_p, C.c_void_p]
         lib.dodrt_host_add_sphere.argtypes = [C.c_void_p, C.c_void_p, C.c_float, C.c_void_p]
@@ -182,10 +183,13 @@ class HostScene:
         )
         if normals:
             out["tri_normals"] = _view(L.dodrt_host_tri_normals(self._h), (z.num_lanes * 8, 9), np.float32)
+            out["tri_attributes"] = _view(L.dodrt_host_tri_attributes(self._h), (z.num_lanes, 80), np.uint32)
+            out["mesh_colors"] = _view(L.dodrt_host_mesh_colors(self._h), (L.dodrt_host_num_meshes(self._h), 3), np.float32)
         return out
 
-    def upload(self, device: int = 0) -> capi.Scene:
-        """Copy the finished scene into one GPU through the C ABI (zero-copy from the host library's arrays)."""
+    def upload(self, device: int = 0, shading: bool = False) -> capi.Scene:
+        """Copy the finished scene into one GPU through the C ABI (zero-copy from the host library's arrays);
+        `shading` also uploads normals / colours for dodrt_render."""
         z = self.sizes()
         L = self._lib
         g = capi.Scene(device)
@@ -206,4 +210,9 @@ class HostScene:
         if z.num_boxes:
             capi._check(cl.dodrt_scene_set_boxes(g._h, C.c_void_p(L.dodrt_host_box_lanes(self._h)), C.c_uint32(z.num_boxes)))
         g.set_epsilon(float(L.dodrt_host_epsilon(self._h)))
+        if shading:
+            capi._check(cl.dodrt_scene_set_shading(
+                g._h, C.c_void_p(L.dodrt_host_tri_attributes(self._h)), C.c_uint32(z.num_lanes),
+                C.c_void_p(L.dodrt_host_mesh_colors(self._h)), C.c_uint32(L.dodrt_host_num_meshes(self._h)),
+                C.c_void_p(L.dodrt_host_sphere_colors(self._h)), C.c_void_p(L.dodrt_host_plane_colors(self._h))))
         return g

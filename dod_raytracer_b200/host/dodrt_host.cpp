@@ -79,8 +79,14 @@ struct Box {
 struct TriLane { // triangle.h:33-44
     float v[9][kLane];
 };
-struct NormalLane { // triangle.h:45-51 without the mesh index: AN, BN, CN per slot
+struct NormalLane { // AN, BN, CN per slot (flat export for tools / tests)
     float n[kLane][9];
+};
+struct AttrLane { // Triangle::Attributes, triangle.h:45-51, byte for byte (320 B)
+    uint32_t meshAttrIdx[kLane];
+    float AN[kLane][3];
+    float BN[kLane][3];
+    float CN[kLane][3];
 };
 
 // glibc's rand()/srand() (TYPE_3 additive feedback generator), restated so that the reference's
@@ -126,6 +132,8 @@ struct dodrt_host_scene {
     uint32_t numTriangles = 0;
     std::vector<TriLane> lanes;       // before build: creation order; after build: re-ordered
     std::vector<NormalLane> normals;  // same order as lanes
+    std::vector<AttrLane> attrs;      // same order as lanes; the reference's own attribute layout
+    std::vector<float> meshColors;    // Mesh::m_meshAttributes, mesh.cpp:23 (3 floats per mesh)
     // kd-tree
     std::vector<uint64_t> nodes;
     std::vector<uint32_t> primNums;
@@ -153,11 +161,20 @@ void pushTriangle(dodrt_host_scene *s, const Vec3 p[3], const Vec3 n[3])
     if (slot == 0) {
         s->lanes.emplace_back();
         s->normals.emplace_back();
+        s->attrs.emplace_back();
         std::memset(&s->lanes.back(), 0, sizeof(TriLane));
         std::memset(&s->normals.back(), 0, sizeof(NormalLane));
+        std::memset(&s->attrs.back(), 0, sizeof(AttrLane)); // emptyTriangleAttributes = {0}, triangle.cpp:265
     }
     TriLane &lane = s->lanes.back();
     NormalLane &nl = s->normals.back();
+    AttrLane &al = s->attrs.back();
+    al.meshAttrIdx[slot] = (uint32_t)(s->meshColors.size() / 3) - 1u; // Mesh::m_meshAttributes.size() - 1, triangle.cpp:286
+    for (int k = 0; k < 3; k++) {
+        al.AN[slot][k] = n[0][k];
+        al.BN[slot][k] = n[1][k];
+        al.CN[slot][k] = n[2][k];
+    }
     for (int c = 0; c < 3; c++) {
         lane.v[c * 3 + 0][slot] = p[c].x;
         lane.v[c * 3 + 1][slot] = p[c].y;
@@ -250,6 +267,8 @@ int addMesh(dodrt_host_scene *s, std::vector<Vec3> &pos, const uint32_t *idx, ui
     }
     std::vector<Vec3> nrm;
     smoothNormals(pos, idx, numTris, nrm);
+    const float meshColor[3] = {(float)0.1, (float)0.8, (float)0.3}; // mesh.cpp:23
+    s->meshColors.insert(s->meshColors.end(), meshColor, meshColor + 3);
     s->lanes.reserve(s->lanes.size() + numTris / kLane + 1);
     s->normals.reserve(s->normals.size() + numTris / kLane + 1);
     for (uint32_t f = 0; f < numTris; f++) {
@@ -709,14 +728,18 @@ int dodrt_host_build_tree(dodrt_host_scene *s)
     // Triangle::reorderLanesByIndices, triangle.cpp:349-367
     std::vector<TriLane> lanes;
     std::vector<NormalLane> normals;
+    std::vector<AttrLane> attrs;
     lanes.reserve(s->primNums.size());
     normals.reserve(s->primNums.size());
+    attrs.reserve(s->primNums.size());
     for (uint32_t idx : s->primNums) {
         lanes.push_back(s->lanes[idx]);
         normals.push_back(s->normals[idx]);
+        attrs.push_back(s->attrs[idx]);
     }
     s->lanes.swap(lanes);
     s->normals.swap(normals);
+    s->attrs.swap(attrs);
     for (int i = 0; i < 3; i++) {
         s->boundsOut[i] = s->bounds.lo[i];
         s->boundsOut[3 + i] = s->bounds.hi[i];
@@ -745,6 +768,9 @@ const float *dodrt_host_tri_lanes(const dodrt_host_scene *s) { return reinterpre
 const uint32_t *dodrt_host_prim_nums(const dodrt_host_scene *s) { return s->primNums.data(); }
 const float *dodrt_host_bounds(const dodrt_host_scene *s) { return s->boundsOut; }
 const float *dodrt_host_tri_normals(const dodrt_host_scene *s) { return reinterpret_cast<const float *>(s->normals.data()); }
+const void *dodrt_host_tri_attributes(const dodrt_host_scene *s) { return s->attrs.data(); }
+const float *dodrt_host_mesh_colors(const dodrt_host_scene *s) { return s->meshColors.data(); }
+uint32_t dodrt_host_num_meshes(const dodrt_host_scene *s) { return (uint32_t)(s->meshColors.size() / 3); }
 const float *dodrt_host_sphere_lanes(const dodrt_host_scene *s) { return s->sphereLanes.data(); }
 const float *dodrt_host_sphere_colors(const dodrt_host_scene *s) { return s->sphereColors.data(); }
 const float *dodrt_host_plane_lanes(const dodrt_host_scene *s) { return s->planeLanes.data(); }

@@ -20,6 +20,11 @@ import numpy as np
 from . import capi, host
 
 LIGHT0 = (0.0, 0.0, -2.0)  # lights[0], main.cpp:284
+# the reference's nine lights: position xyz, intensity (main.cpp:283-292)
+REFERENCE_LIGHTS = ((0.0, 0.0, -2.0, 3.0), (4.0, 4.3, 3.3, 1.0), (-4.0, -2.95, 3.95, 1.0), (3.95, -4.2, 3.3, 1.0),
+                    (-2.9, 4.2, 3.8, 1.0), (3.95, 2.8, -4.3, 1.0), (-3.0, -3.8, -3.3, 1.0), (4.2, -4.2, -3.4, 1.0),
+                    (-2.9, 4.4, -3.5, 1.0))
+REFERENCE_DEPTH = 10  # recursionDepth, main.cpp:301
 CLS_REFERENCE = capi.CLS_SPHERE | capi.CLS_PLANE | capi.CLS_CYLINDER | capi.CLS_TREE
 
 

@@ -61,7 +61,8 @@ extern "C" {
 #define DODRT_CLS_BOX 16u
 #define DODRT_CLS_ALL 31u
 
-#define DODRT_RAY_ANY 1u /* _Intersect::returnOnAny, base_shape.h:12 */
+#define DODRT_RAY_ANY 1u  /* _Intersect::returnOnAny, base_shape.h:12 */
+#define DODRT_RAY_SKIP 2u /* inactive slot of a batch: answered with DODRT_MISS without any work */
 
 /* One query = the reference's `_Intersect` (base_shape.h:8-15) without the HitRecord reference. */
 typedef struct dodrt_ray {
@@ -141,6 +142,15 @@ DODRT_API int dodrt_scene_set_boxes(dodrt_scene *scene, const float *box_lanes, 
 /* Config::Epsilon (config.h:9), used by the plane and cylinder tests; default 1e-4 */
 DODRT_API int dodrt_scene_set_epsilon(dodrt_scene *scene, float epsilon);
 
+/* Shading attributes for dodrt_render*: Triangle::m_triangleAttributes after the re-order, in the reference's own
+ * layout (triangle.h:45-51: 320 bytes per lane = unsigned meshAttrIdx[8], vec3 AN[8], vec3 BN[8], vec3 CN[8]),
+ * Mesh::m_meshAttributes colours (mesh.h:13-16, 3 floats per mesh), and the colours the spheres / planes were
+ * created with (sphere.h:14-17, plane.h:14-17; 3 floats each, creation order).  Cylinders render black like in the
+ * reference (cylinder.cpp:172-179,204). */
+DODRT_API int dodrt_scene_set_shading(dodrt_scene *scene, const void *tri_attributes, uint32_t num_tri_lanes,
+                                      const float *mesh_colors, uint32_t num_meshes, const float *sphere_colors,
+                                      const float *plane_colors);
+
 /* Tuning / A-B knob: which traversal kernel variant answers the queries (all variants return identical
  * results; see dod_raytracer_b200/csrc/dodrt_kernels.cu).  variant < 0 restores the default. */
 DODRT_API int dodrt_scene_set_kernel_variant(dodrt_scene *scene, int variant);
@@ -165,6 +175,15 @@ DODRT_API int dodrt_trace_shadow(dodrt_scene *scene, const dodrt_frame *frame, c
 DODRT_API int dodrt_trace_frame(dodrt_scene *scene, const dodrt_frame *frame, const float *xs, const float *ys,
                       const float *lights /* num_lights x 3 */, uint32_t num_lights, dodrt_hit *hits,
                       uint8_t *visible);
+
+/* dodrt_render replaces rayTrace (main.cpp:273-347) for the whole frame: per pixel up to `depth` mirror bounces
+ * (the reference hard-codes 10, main.cpp:301), each = closest-hit chain + one canSeeLight query per light + the
+ * reference's shading (main.cpp:156-244), blended with weight 1/2^k; rgb is width*height*3 bytes, row-major
+ * (what the reference hands to stbi_write_png, main.cpp:396).  lights: num_lights x {x, y, z, intensity}
+ * (light.h:4-8; the reference's nine are main.cpp:283-292), num_lights <= 16.  frame->classes selects the shape
+ * classes; tiles/compact are ignored (one GPU renders the whole frame). */
+DODRT_API int dodrt_render(dodrt_scene *scene, const dodrt_frame *frame, const float *xs, const float *ys,
+                           const float *lights, uint32_t num_lights, uint32_t depth, uint8_t *rgb);
 
 /* ---- queries: device-resident buffers (pointers in the scene's GPU memory, asynchronous on
  * `stream`, a cudaStream_t passed as void*; NULL = the default stream).  Used when the caller keeps

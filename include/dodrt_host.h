@@ -96,6 +96,11 @@ DODRT_API const float *dodrt_host_tri_lanes(const dodrt_host_scene *scene);    /
 DODRT_API const uint32_t *dodrt_host_prim_nums(const dodrt_host_scene *scene); /* original lane of each lane */
 DODRT_API const float *dodrt_host_bounds(const dodrt_host_scene *scene);       /* 6 floats */
 DODRT_API const float *dodrt_host_tri_normals(const dodrt_host_scene *scene);  /* re-ordered, 9 floats / slot */
+/* shading attributes: Triangle::m_triangleAttributes after the re-order, byte for byte (triangle.h:45-51: 320 B per
+ * lane = meshAttrIdx[8], AN[8] BN[8] CN[8] as vec3), and Mesh::m_meshAttributes (one colour per mesh, mesh.cpp:23) */
+DODRT_API const void *dodrt_host_tri_attributes(const dodrt_host_scene *scene);
+DODRT_API const float *dodrt_host_mesh_colors(const dodrt_host_scene *scene);
+DODRT_API uint32_t dodrt_host_num_meshes(const dodrt_host_scene *scene);
 DODRT_API const float *dodrt_host_sphere_lanes(const dodrt_host_scene *scene);
 DODRT_API const float *dodrt_host_sphere_colors(const dodrt_host_scene *scene); /* 3 floats / sphere */
 DODRT_API const float *dodrt_host_plane_lanes(const dodrt_host_scene *scene);

@@ -326,6 +326,21 @@ void ref_normals_export(float *normals)
     }
 }
 
+// Triangle::m_triangleAttributes (re-ordered) byte for byte, 320 B per lane, and the mesh colours
+void ref_attrs_export(void *attrs, float *meshColors)
+{
+    const std::vector<Triangle::Attributes> &a = g_probe ? g_realTriAttrs : Triangle::m_triangleAttributes;
+    const std::vector<Mesh::Attributes> &m = g_probe ? g_realMeshAttrs : Mesh::m_meshAttributes;
+    static_assert(sizeof(Triangle::Attributes) == 320, "attribute layout");
+    std::memcpy(attrs, a.data(), a.size() * sizeof(Triangle::Attributes));
+    for (size_t i = 0; i < m.size(); i++) {
+        meshColors[i * 3 + 0] = m[i].color.x;
+        meshColors[i * 3 + 1] = m[i].color.y;
+        meshColors[i * 3 + 2] = m[i].color.z;
+    }
+}
+uint32_t ref_num_meshes() { return static_cast<uint32_t>((g_probe ? g_realMeshAttrs : Mesh::m_meshAttributes).size()); }
+
 uint32_t ref_num_spheres() { return static_cast<uint32_t>(g_spheres.size()); }
 // x, y, z, radius, r, g, b per sphere (shadow copy of what went through Sphere::create)
 void ref_spheres_export(float *out)

@@ -153,5 +153,18 @@ def main():
         print(f, os.path.getsize(os.path.join(HERE, f)))
 
 
+
+
+def render_fixture():
+    """The reference's own rayTrace (main.cpp:273-347: 9 lights, 10 bounces, all shape classes) on the srand(1)
+    teapot scene, one band starting at row 0 (canonical raster tables), 240x135."""
+    ref = build_ref(os.path.join(HERE, "teapot.dodm"))
+    img = ref.render(240, 135, nthreads=1)
+    np.savez_compressed(os.path.join(HERE, "teapot_render_240x135.npz"), rgb=img)
+    print("render fixture", img.shape, float(img.mean()))
+
+
 if __name__ == "__main__":
-    main()
+    if not os.environ.get("DODRT_GOLDEN_RENDER_ONLY"):
+        main()
+    render_fixture()

@@ -228,6 +228,15 @@ class RefLib:
         self.lib.ref_normals_export(_ptr(out))
         return out
 
+    def export_attributes(self):
+        """(Triangle::Attributes lanes as uint32 [lanes, 80], mesh colours [meshes, 3])"""
+        sz = self.tree_sizes()
+        self.lib.ref_num_meshes.restype = C.c_uint32
+        attrs = np.zeros((sz["lanes"], 80), np.uint32)
+        colors = np.zeros((self.lib.ref_num_meshes(), 3), np.float32)
+        self.lib.ref_attrs_export(_ptr(attrs), _ptr(colors))
+        return attrs, colors
+
     def export_spheres(self):
         n = self.lib.ref_num_spheres()
         out = np.zeros((n, 7), np.float32)

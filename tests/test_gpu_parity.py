@@ -224,3 +224,50 @@ def test_against_the_reference_code_directly():
             pts = hit_points(rays, want["t"])
             sr = ref.shadow_rays(pts, LIGHT0)
             assert (g.intersect(sr, cls)["prim"] == ref.intersect(sr, cls, 8)["prim"]).all()
+
+
+# ---- shading + 10-bounce loop on the GPU vs the reference's own rayTrace --------------------
+def _render_scene():
+    from dod_raytracer_b200 import host
+    hs = host.HostScene()
+    hs.add_reference_scene(1, 16)
+    hs.add_mesh_file(f"{GOLDEN}/teapot.dodm")
+    hs.build_tree()
+    return hs
+
+
+def test_full_reference_frame_pixels_within_one_255th():
+    """north_star: 'final 8-bit pixels must be within 1/255'.  Fixture = the UNMODIFIED reference rayTrace
+    (9 lights, 10 mirror bounces, spheres + planes + cylinder + teapot kd-tree) rendered by oracle/_ref."""
+    from dod_raytracer_b200 import host, workloads
+    want = np.load(f"{GOLDEN}/teapot_render_240x135.npz")["rgb"].astype(np.int32)
+    h, w = want.shape[:2]
+    xs, ys = host.ray_tables(w, h)
+    for variant in (3, 0, 4):
+        with _render_scene().upload(0, shading=True) as g:
+            g.set_kernel_variant(variant)
+            got = g.render(capi.Frame.make(w, h, classes=ALL), xs, ys, workloads.REFERENCE_LIGHTS,
+                           workloads.REFERENCE_DEPTH).astype(np.int32)
+        diff = np.abs(got - want)
+        assert diff.max() <= 1, f"variant {variant}: max pixel difference {diff.max()} at {np.argwhere(diff > 1)[:5]}"
+        assert (diff == 0).mean() > 0.999, f"variant {variant}: only {(diff == 0).mean():.5f} of the channels identical"
+
+
+@pytest.mark.skipif(not have_ref(), reason="oracle/_ref not present")
+def test_render_against_live_reference_other_sizes_and_depths():
+    from dod_raytracer_b200 import host, workloads
+    ref = RefLib()
+    ref.add_reference_spheres(1, 16)
+    ref.add_reference_planes()
+    ref.add_reference_cylinder()
+    ref.add_mesh(f"{GOLDEN}/teapot.dodm")
+    ref.build_tree()
+    with _render_scene().upload(0, shading=True) as g:
+        for (w, h) in ((160, 90), (97, 61)):
+            want = ref.render(w, h, nthreads=1).astype(np.int32)  # one band: canonical raster tables
+            xs, ys = host.ray_tables(w, h)
+            got = g.render(capi.Frame.make(w, h, classes=ALL), xs, ys, workloads.REFERENCE_LIGHTS, 10).astype(np.int32)
+            assert np.abs(got - want).max() <= 1
+        # depth 1 (primary + 9 shadow passes) is still a sane image and differs from depth 10
+        d1 = g.render(capi.Frame.make(160, 90, classes=ALL), *host.ray_tables(160, 90), workloads.REFERENCE_LIGHTS, 1)
+        assert d1.mean() > 10 and np.abs(d1.astype(np.int32) - ref.render(160, 90, nthreads=1)).max() > 1
