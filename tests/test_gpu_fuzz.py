@@ -1,0 +1,84 @@
+"""GPU (-m gpu): randomised scenes and rays -- triangle soups with degenerate / duplicated / axis-aligned
+triangles, ragged lane counts, tiny and huge coordinates, rays with zero direction components and origins on
+vertices -- built with the product's host builder and answered by the CUDA path and by the oracle.  Bit-exact."""
+import numpy as np
+import pytest
+
+from dod_raytracer_b200 import capi, host
+from gpu_util import assert_hits_equal
+from oracle_api import CLS_BOX, CLS_CYLINDER, CLS_PLANE, CLS_SPHERE, CLS_TREE, CYL_DT, RAY_ANY, Scene, pack_lanes
+from scenes import make_rays
+
+pytestmark = pytest.mark.gpu
+EVERYTHING = CLS_SPHERE | CLS_PLANE | CLS_CYLINDER | CLS_TREE | CLS_BOX
+
+
+def random_soup(rng, n, scale):
+    """n triangles around the origin; ~10 % degenerate (zero area), ~10 % duplicates, ~10 % axis-aligned."""
+    c = (rng.rand(n, 1, 3).astype(np.float32) - np.float32(0.5)) * np.float32(4.0 * scale)
+    tri = c + (rng.rand(n, 3, 3).astype(np.float32) - np.float32(0.5)) * np.float32(0.8 * scale)
+    k = max(1, n // 10)
+    tri[:k, 2] = tri[:k, 1]                      # degenerate: two equal vertices
+    tri[k:2 * k] = tri[2 * k:3 * k]              # exact duplicates
+    tri[3 * k:4 * k, :, 2] = tri[3 * k:4 * k, :1, 2]  # flat in z (axis-aligned plane)
+    pos = tri.reshape(-1, 3)
+    idx = np.arange(n * 3, dtype=np.uint32).reshape(n, 3)
+    return pos, idx
+
+
+def random_rays(rng, n, scale, verts):
+    o = (rng.rand(n, 3).astype(np.float32) - np.float32(0.5)) * np.float32(8.0 * scale)
+    d = rng.randn(n, 3).astype(np.float32)
+    d[::7, 0] = 0.0                               # axis-parallel components: inv = +-inf, NaN slabs
+    d[::11, 1] = 0.0
+    d[::13, 2] = -0.0
+    d[5::97] = [0.0, 0.0, 1.0]
+    norm = np.sqrt((d * d).sum(axis=1, dtype=np.float32)).astype(np.float32)
+    norm[norm == 0] = 1
+    d = (d / norm[:, None]).astype(np.float32)
+    o[3::17] = verts[rng.randint(0, len(verts), size=len(o[3::17]))]  # origins exactly on mesh vertices
+    rays = make_rays(o, d)
+    rays["clip"][::3] = (rng.rand(len(rays["clip"][::3])) * 6 * scale).astype(np.float32)
+    rays["clip"][4::29] = 0.0
+    rays["flags"][1::5] = RAY_ANY
+    return rays
+
+
+@pytest.mark.parametrize("seed,ntri,scale", [(1, 5, 1.0), (2, 37, 1.0), (3, 400, 1.0), (4, 3000, 1.0), (5, 1500, 1e-3),
+                                             (6, 1500, 1e4), (7, 9, 1.0), (8, 20000, 1.0)])
+def test_random_scene_matches_oracle(oracle, seed, ntri, scale):
+    rng = np.random.RandomState(seed)
+    pos, idx = random_soup(rng, ntri, scale)
+    hs = host.HostScene()
+    hs.add_mesh(pos, idx)
+    nsph, nbox, npl = rng.randint(0, 20), rng.randint(0, 20), rng.randint(0, 10)
+    spheres = np.concatenate([(rng.rand(nsph, 3) - 0.5) * 6 * scale, rng.rand(nsph, 1) * 0.5 * scale], axis=1).astype(np.float32)
+    lo = ((rng.rand(nbox, 3) - 0.5) * 6 * scale).astype(np.float32)
+    boxes = np.concatenate([lo, lo + (rng.rand(nbox, 3) * scale).astype(np.float32)], axis=1).astype(np.float32)
+    nrm = rng.randn(npl, 3).astype(np.float32)
+    nrm /= np.sqrt((nrm * nrm).sum(axis=1, keepdims=True)).astype(np.float32) if npl else 1
+    planes = np.concatenate([((rng.rand(npl, 3) - 0.5) * 8 * scale).astype(np.float32), nrm], axis=1).astype(np.float32)
+    for s in spheres:
+        hs.add_sphere(s[:3], float(s[3]))
+    for b in boxes:
+        hs.add_box(b[:3], b[3:])
+    hs.build_tree()
+    a = hs.arrays()
+    cyl = np.zeros(1, CYL_DT)
+    cyl["base"], cyl["axis"], cyl["radius_sq"], cyl["height"] = [0.3 * scale, -scale, 0], [0, 1, 0], (0.4 * scale) ** 2, 2 * scale
+    scene = Scene(a["nodes"], a["tri_lanes"], a["bounds"], spheres=spheres, planes=planes, cylinders=cyl, boxes=boxes)
+    assert scene.sphere_lanes.tobytes() == a["sphere_lanes"].tobytes() and scene.box_lanes.tobytes() == a["box_lanes"].tobytes()
+    rays = random_rays(rng, 40000, scale, pos)
+    g = hs.upload(0)
+    g.set_planes(pack_lanes(planes), npl)
+    g.set_cylinders(cyl)
+    try:
+        for variant in (3, 0, 4, 5):
+            g.set_kernel_variant(variant)
+            for cls in (EVERYTHING, CLS_TREE):
+                want = oracle.intersect(scene, rays, cls, nthreads=8)
+                assert_hits_equal(g.intersect(rays, cls), want, rays=rays, what=f"seed {seed} variant {variant} classes {cls}")
+    finally:
+        g.close()
+    hit_rate = (want["prim"] != 0xFFFFFFFF).mean()
+    assert 0.0 <= hit_rate <= 1.0
