@@ -46,6 +46,7 @@ def parse_args():
     ap.add_argument("--tile", default="32x32")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-render", action="store_true", help="skip the reference's as-is frame (9 lights, 10 bounces)")
     return ap.parse_args()
 
 
@@ -423,6 +424,36 @@ def main():
         parity = {"against": cpu.kind, "t_bit_mismatches": int((t_gpu.view(np.uint32) != t_cpu.view(np.uint32)).sum()),
                   "visibility_mismatches": int((gpu_vis != vis_cpu).sum()) if nl else 0, "rays": int(r)}
 
+    # ---- the reference's as-is frame (rayTrace, main.cpp:273-347: 9 lights, 10 bounces) at config.ini's 1920x1080 ------
+    reference_frame = None
+    if world == 1 and not args.no_render and not args.no_cpu_baseline and w.reference_scene and w.mesh != "none":
+        try:
+            rw, rh = 1920, 1080
+            rscene = hs.upload(local_rank, shading=True)
+            rxs, rys = host.ray_tables(rw, rh)
+            rframe = capi.Frame.make(rw, rh, classes=workloads.CLS_REFERENCE)
+            rgb = torch.empty((rh, rw, 3), dtype=torch.uint8, pin_memory=True).numpy()
+            rscene.render(rframe, rxs, rys, workloads.REFERENCE_LIGHTS, workloads.REFERENCE_DEPTH, rgb)
+            best = None
+            for _ in range(3):
+                t1 = time.perf_counter()
+                rscene.render(rframe, rxs, rys, workloads.REFERENCE_LIGHTS, workloads.REFERENCE_DEPTH, rgb)
+                dt = time.perf_counter() - t1
+                best = dt if best is None else min(best, dt)
+            rscene.close()
+            queries = rw * rh * workloads.REFERENCE_DEPTH * (1 + len(workloads.REFERENCE_LIGHTS))
+            reference_frame = {"what": "rayTrace as the reference ships it: 1920x1080, 9 lights, 10 mirror bounces, all shape "
+                                       "classes, 8-bit RGB to the host (dodrt_render)", "ray_queries": queries,
+                               "gpu_frame_ms": best * 1e3, "gpu_mrays_s": queries / best / 1e6}
+            if cpu.kind == "reference":
+                with quiet_stdout():
+                    t1 = time.perf_counter()
+                    cpu.ref.render(rw, rh, nthreads=cpu.cores)
+                    cpu_s = time.perf_counter() - t1
+                reference_frame.update(cpu_frame_ms=cpu_s * 1e3, cpu_cores=cpu.cores, speedup=cpu_s / best)
+        except Exception as exc:  # never lose the headline line over the extra
+            reference_frame = {"error": repr(exc)}
+
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
             "data": "synthetic",
@@ -435,7 +466,7 @@ def main():
                        "l2": "flushed between steps (512 MiB memset outside the per-step event bracket)",
                        "host_build_s": round(build_s, 2), "wall_s_timed_region": round(wall, 3)},
             "e2e": e2e, "gpu_launches": launches, "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu_baseline,
-            "parity": parity, "frame_ms": ms_per_step}
+            "parity": parity, "frame_ms": ms_per_step, "reference_frame": reference_frame}
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.barrier()
