@@ -5,6 +5,7 @@
 // error translation.  All ray/shape arithmetic lives in dodrt_device.cuh / dodrt_kernels.cu.
 // There is deliberately no CPU implementation behind any entry point.
 #include "dodrt_kernels.cuh"
+#include "dodrt_prim_bvh.cuh"
 
 #include <atomic>
 #include <cmath>
@@ -82,6 +83,8 @@ struct dodrt_scene {
     float *d_planes = nullptr;
     dodrt_cylinder *d_cylinders = nullptr;
     float *d_boxes = nullptr;
+    float4 *d_sphereBvh = nullptr, *d_boxBvh = nullptr;
+    uint32_t *d_sphereBvhIds = nullptr, *d_boxBvhIds = nullptr;
     uint32_t *d_triAttrs = nullptr;
     float *d_meshColors = nullptr, *d_sphereColors = nullptr, *d_planeColors = nullptr;
     unsigned long long *d_counters = nullptr;
@@ -325,6 +328,10 @@ int dodrt_scene_destroy(dodrt_scene *s)
     freeDevice(s->d_planes);
     freeDevice(s->d_cylinders);
     freeDevice(s->d_boxes);
+    freeDevice(s->d_sphereBvh);
+    freeDevice(s->d_sphereBvhIds);
+    freeDevice(s->d_boxBvh);
+    freeDevice(s->d_boxBvhIds);
     freeDevice(s->d_triAttrs);
     freeDevice(s->d_meshColors);
     freeDevice(s->d_sphereColors);
@@ -412,10 +419,47 @@ static int uploadLanes(dodrt_scene *s, float **slot, const float **view, uint32_
     return DODRT_OK;
 }
 
+// Builds and uploads the culling BVH over `count` primitives whose boxes are given as count x {min xyz, max xyz}.
+static int uploadPrimBvh(dodrt_scene *s, const std::vector<float> &boxes, uint32_t count, float4 **d_nodes, uint32_t **d_ids,
+                         const float4 **nodesView, const uint32_t **idsView)
+{
+    std::lock_guard<std::mutex> lock(s->mutex);
+    DeviceGuard guard(s->device);
+    if (!guard.ok) return fail(DODRT_E_CUDA, "cannot select device %d", s->device);
+    freeDevice(*d_nodes);
+    freeDevice(*d_ids);
+    *nodesView = nullptr;
+    *idsView = nullptr;
+    static const bool enabled = [] { const char *e = std::getenv("DODRT_PRIM_BVH"); return !e || std::atoi(e) != 0; }();
+    if (!enabled || count < kPrimBvhMinCount) return DODRT_OK;
+    std::vector<PrimBvhNode> nodes;
+    std::vector<uint32_t> ids;
+    build_prim_bvh(boxes.data(), count, nodes, ids);
+    CUDA_TRY(cudaMalloc(d_nodes, nodes.size() * sizeof(PrimBvhNode)));
+    CUDA_TRY(cudaMemcpy(*d_nodes, nodes.data(), nodes.size() * sizeof(PrimBvhNode), cudaMemcpyHostToDevice));
+    CUDA_TRY(cudaMalloc(d_ids, ids.size() * sizeof(uint32_t)));
+    CUDA_TRY(cudaMemcpy(*d_ids, ids.data(), ids.size() * sizeof(uint32_t), cudaMemcpyHostToDevice));
+    *nodesView = *d_nodes;
+    *idsView = *d_ids;
+    return DODRT_OK;
+}
+
 int dodrt_scene_set_spheres(dodrt_scene *s, const float *sphere_lanes, uint32_t num_spheres)
 {
     if (!s) return fail(DODRT_E_INVALID, "scene is NULL");
-    return uploadLanes(s, &s->d_spheres, &s->dev.sphere_lanes, &s->dev.num_spheres, sphere_lanes, num_spheres, 4 * kLane);
+    int rc = uploadLanes(s, &s->d_spheres, &s->dev.sphere_lanes, &s->dev.num_spheres, sphere_lanes, num_spheres, 4 * kLane);
+    if (rc != DODRT_OK) return rc;
+    std::vector<float> boxes((size_t)num_spheres * 6);
+    for (uint32_t i = 0; i < num_spheres; i++) { // box of sphere i: centre +- radius (radius from radiusSq, rounded up)
+        const float *lane = sphere_lanes + (size_t)(i / kLane) * 4 * kLane;
+        const uint32_t j = i % kLane;
+        const float r = std::sqrt(lane[3 * kLane + j]) * 1.000001f;
+        for (int k = 0; k < 3; k++) {
+            boxes[(size_t)i * 6 + k] = lane[k * kLane + j] - r;
+            boxes[(size_t)i * 6 + 3 + k] = lane[k * kLane + j] + r;
+        }
+    }
+    return uploadPrimBvh(s, boxes, num_spheres, &s->d_sphereBvh, &s->d_sphereBvhIds, &s->dev.sphere_bvh, &s->dev.sphere_bvh_ids);
 }
 
 int dodrt_scene_set_planes(dodrt_scene *s, const float *plane_lanes, uint32_t num_planes)
@@ -427,7 +471,19 @@ int dodrt_scene_set_planes(dodrt_scene *s, const float *plane_lanes, uint32_t nu
 int dodrt_scene_set_boxes(dodrt_scene *s, const float *box_lanes, uint32_t num_boxes)
 {
     if (!s) return fail(DODRT_E_INVALID, "scene is NULL");
-    return uploadLanes(s, &s->d_boxes, &s->dev.box_lanes, &s->dev.num_boxes, box_lanes, num_boxes, 6 * kLane);
+    int rc = uploadLanes(s, &s->d_boxes, &s->dev.box_lanes, &s->dev.num_boxes, box_lanes, num_boxes, 6 * kLane);
+    if (rc != DODRT_OK) return rc;
+    std::vector<float> boxes((size_t)num_boxes * 6);
+    for (uint32_t i = 0; i < num_boxes; i++) {
+        const float *lane = box_lanes + (size_t)(i / kLane) * 6 * kLane;
+        const uint32_t j = i % kLane;
+        for (int k = 0; k < 3; k++) { // tolerate inverted boxes (min > max): the slab test swaps per axis anyway
+            const float a = lane[k * kLane + j], b = lane[(3 + k) * kLane + j];
+            boxes[(size_t)i * 6 + k] = a < b ? a : b;
+            boxes[(size_t)i * 6 + 3 + k] = a < b ? b : a;
+        }
+    }
+    return uploadPrimBvh(s, boxes, num_boxes, &s->d_boxBvh, &s->d_boxBvhIds, &s->dev.box_bvh, &s->dev.box_bvh_ids);
 }
 
 int dodrt_scene_set_cylinders(dodrt_scene *s, const dodrt_cylinder *cylinders, uint32_t num_cylinders)

@@ -42,6 +42,11 @@ struct DeviceScene {
     const float *box_lanes;    // minx miny minz maxx maxy maxz [8]
     uint32_t num_boxes;
     float epsilon;
+    // optional exact culling BVHs over the sphere / box lanes (dodrt_prim_bvh.cuh); nullptr = brute force
+    const float4 *sphere_bvh;
+    const uint32_t *sphere_bvh_ids;
+    const float4 *box_bvh;
+    const uint32_t *box_bvh_ids;
     // shading attributes (only read by the render kernels): Triangle::m_triangleAttributes in the reference's
     // layout (80 words per lane, triangle.h:45-51), one colour per mesh / sphere / plane
     const uint32_t *tri_attrs;

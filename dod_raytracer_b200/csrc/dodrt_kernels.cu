@@ -23,6 +23,7 @@
 //      refilled (dodrt_pool_kernel.inl).
 // Every variant computes identical results (parity tests run all of them).
 #include "dodrt_kernels.cuh"
+#include "dodrt_prim_bvh.cuh"
 
 #include <cstdlib>
 
@@ -357,13 +358,17 @@ __device__ __forceinline__ bool analytic_chain(const DeviceScene &s, uint32_t cl
                                                const float d[3], bool any, float &clip, Hit &hit, bool &found)
 {
     Hit h;
-    if ((classes & DODRT_CLS_SPHERE) && s.num_spheres && sphere_query(s, o, d, any, clip, h)) {
+    if ((classes & DODRT_CLS_SPHERE) && s.num_spheres &&
+        (s.sphere_bvh ? prim_bvh_query<DODRT_KIND_SPHERE>(s.sphere_bvh, s.sphere_bvh_ids, s.sphere_lanes, o, d, any, clip, h)
+                      : sphere_query(s, o, d, any, clip, h))) {
         hit = h;
         found = true;
         if (any) return true;
         clip = h.t;
     }
-    if ((classes & DODRT_CLS_BOX) && s.num_boxes && box_query(s, o, d, any, clip, h)) {
+    if ((classes & DODRT_CLS_BOX) && s.num_boxes &&
+        (s.box_bvh ? prim_bvh_query<DODRT_KIND_BOX>(s.box_bvh, s.box_bvh_ids, s.box_lanes, o, d, any, clip, h)
+                   : box_query(s, o, d, any, clip, h))) {
         hit = h;
         found = true;
         if (any) return true;

@@ -82,3 +82,29 @@ def test_random_scene_matches_oracle(oracle, seed, ntri, scale):
         g.close()
     hit_rate = (want["prim"] != 0xFFFFFFFF).mean()
     assert 0.0 <= hit_rate <= 1.0
+
+
+@pytest.mark.parametrize("seed,count,scale", [(11, 64, 1.0), (12, 777, 1.0), (13, 5000, 1.0), (14, 3000, 1e-2), (15, 3000, 1e3)])
+def test_sphere_box_culling_bvh_is_exact(oracle, seed, count, scale):
+    """>= 64 spheres / boxes switch the CUDA path from the reference's brute force to the culling BVH
+    (dodrt_prim_bvh.cuh); the answer must stay the brute-force answer (lexicographic min of (t, id)), including
+    overlapping and nested primitives, origins inside primitives, ties between identical primitives."""
+    rng = np.random.RandomState(seed)
+    c = ((rng.rand(count, 3) - 0.5) * 9 * scale).astype(np.float32)
+    r = ((0.03 + rng.rand(count, 1) * 0.3) * scale).astype(np.float32)
+    spheres = np.concatenate([c, r], axis=1).astype(np.float32)
+    spheres[1::50] = spheres[0::50][: len(spheres[1::50])]  # exact duplicates: the lower id must win
+    spheres[7::90, 3] *= 12  # a few big ones that contain many others (and many ray origins)
+    lo = ((rng.rand(count, 3) - 0.5) * 9 * scale).astype(np.float32)
+    boxes = np.concatenate([lo, lo + ((0.02 + rng.rand(count, 3) * 0.5) * scale).astype(np.float32)], axis=1).astype(np.float32)
+    boxes[3::40] = boxes[2::40][: len(boxes[3::40])]
+    boxes[5::120, 3:] += np.float32(4 * scale)
+    scene = Scene(spheres=spheres, boxes=boxes)
+    rays = random_rays(rng, 60000, scale, c)
+    with capi.Scene(0) as g:
+        g.set_spheres(scene.sphere_lanes, count)
+        g.set_boxes(scene.box_lanes, count)
+        for cls in (CLS_SPHERE, CLS_BOX, CLS_SPHERE | CLS_BOX):
+            want = oracle.intersect(scene, rays, cls, nthreads=8)
+            assert_hits_equal(g.intersect(rays, cls), want, rays=rays, what=f"seed {seed} classes {cls}")
+            assert (want["prim"] != 0xFFFFFFFF).mean() > 0.02
