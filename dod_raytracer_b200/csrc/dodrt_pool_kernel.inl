@@ -58,6 +58,83 @@ __device__ __forceinline__ void write_result(const TraceParams &p, uint64_t out,
     }
 }
 
+// Stage A for one work item: build the ray, run the analytic classes (Sphere -> [Box] -> Plane -> Cylinder), test
+// the kd-tree bounds.  A ray that does not need the tree is FINISHED here (its result is written); returns true,
+// with `r` filled, when the ray has to traverse the tree.
+template <int MODE>
+__device__ __forceinline__ bool stage_a(const TraceParams &p, bool useTree, uint64_t item, PoolRay &r)
+{
+    const DeviceScene &s = p.scene;
+    const bool inRange = item < p.count;
+    r.o[0] = r.o[1] = r.o[2] = 0.0f;
+    r.d[0] = r.d[1] = 0.0f, r.d[2] = 1.0f;
+    r.clip = 0.0f, r.flags = 0u;
+    r.tmin = r.tmax = 0.0f;
+    bool valid = false;  // there is a ray to trace
+    bool writes = false; // this lane owns a result slot
+    uint64_t slot = item;
+    if (MODE == kModeRays) {
+        if (inRange) {
+            const float4 *src = reinterpret_cast<const float4 *>(p.rays + item);
+            const float4 a = __ldg(src), b = __ldg(src + 1);
+            r.o[0] = a.x, r.o[1] = a.y, r.o[2] = a.z;
+            r.d[0] = a.w, r.d[1] = b.x, r.d[2] = b.y;
+            r.clip = b.z;
+            r.flags = __float_as_uint(b.w) & DODRT_RAY_ANY;
+            writes = true;
+            valid = (__float_as_uint(b.w) & DODRT_RAY_SKIP) == 0u;
+        }
+    } else {
+        uint32_t col = 0, row = 0;
+        uint64_t compactSlot = 0;
+        const bool inside = inRange && slot_to_pixel(p.frame, p.tiles_x, p.tile_order, item, col, row, compactSlot);
+        slot = p.frame.compact ? compactSlot : (uint64_t)row * p.frame.width + col;
+        writes = inside || (inRange && p.frame.compact);
+        r.o[0] = p.frame.origin[0], r.o[1] = p.frame.origin[1], r.o[2] = p.frame.origin[2];
+        if (inside) {
+            primary_dir(__ldg(p.xs + col), __ldg(p.ys + row), r.d);
+        }
+        if (MODE == kModePrimary) {
+            valid = inside;
+            r.clip = kInfinity;
+        } else {
+            r.flags = DODRT_RAY_ANY;
+            if (inside) {
+                const float4 ph = reinterpret_cast<const float4 *>(p.hits)[slot];
+                if (__float_as_uint(ph.y) != DODRT_MISS) {
+                    float so[3], sd[3];
+                    shadow_ray(r.o, r.d, ph.x, p.light, so, sd, r.clip);
+                    r.o[0] = so[0], r.o[1] = so[1], r.o[2] = so[2];
+                    r.d[0] = sd[0], r.d[1] = sd[1], r.d[2] = sd[2];
+                    valid = true;
+                }
+            }
+        }
+    }
+    const bool rayAny = (r.flags & DODRT_RAY_ANY) != 0u;
+    const float rayClip0 = r.clip;
+    Hit h;
+    h.t = r.clip, h.prim = DODRT_MISS, h.u = h.v = 0.0f;
+    bool aFound = false, decided = !valid;
+    if (valid) {
+        decided = analytic_chain(s, p.classes, r.o, r.d, rayAny, r.clip, h, aFound);
+    }
+    bool survive = false;
+    if (!decided && useTree) {
+        const float inv[3] = {1.0f / r.d[0], 1.0f / r.d[1], 1.0f / r.d[2]};
+        survive = slab(s.bmin, s.bmax, r.o, inv, r.clip, r.tmin, r.tmax) && !(r.tmin > r.clip);
+    }
+    if (writes && !survive) { // finished without the kd-tree
+        const bool blocked = (MODE == kModeShadow) ? (!valid || aFound) : aFound;
+        write_result<MODE>(p, slot, rayAny, rayClip0, h, blocked);
+    }
+    r.hitT = h.t;
+    r.hitPrim = h.prim;
+    r.out = (uint32_t)slot;
+    r.flags |= (uint32_t)(slot >> 32) << 1;
+    return survive;
+}
+
 template <int MODE> __global__ void __launch_bounds__(32 * kWarpsPerBlock) trace_kernel_pool(const TraceParams p)
 {
     __shared__ uint32_t poolMem[kWarpsPerBlock][kPoolCap * kPoolWords];
@@ -101,75 +178,10 @@ template <int MODE> __global__ void __launch_bounds__(32 * kWarpsPerBlock) trace
                 exhausted = true;
                 break;
             }
-            const uint64_t item = base + lane;
-            const bool inRange = item < p.count;
             PoolRay r;
-            r.o[0] = r.o[1] = r.o[2] = 0.0f;
-            r.d[0] = r.d[1] = 0.0f, r.d[2] = 1.0f;
-            r.clip = 0.0f, r.flags = 0u;
-            bool valid = false;      // there is a ray to trace
-            bool writes = false;     // this lane owns a result slot
-            uint64_t slot = item;
-            if (MODE == kModeRays) {
-                if (inRange) {
-                    const float4 *src = reinterpret_cast<const float4 *>(p.rays + item);
-                    const float4 a = __ldg(src), b = __ldg(src + 1);
-                    r.o[0] = a.x, r.o[1] = a.y, r.o[2] = a.z;
-                    r.d[0] = a.w, r.d[1] = b.x, r.d[2] = b.y;
-                    r.clip = b.z;
-                    r.flags = __float_as_uint(b.w) & DODRT_RAY_ANY;
-                    valid = writes = true;
-                }
-            } else {
-                uint32_t col = 0, row = 0;
-                uint64_t compactSlot = 0;
-                const bool inside = inRange && slot_to_pixel(p.frame, p.tiles_x, p.tile_order, item, col, row, compactSlot);
-                slot = p.frame.compact ? compactSlot : (uint64_t)row * p.frame.width + col;
-                writes = inside || (inRange && p.frame.compact);
-                r.o[0] = p.frame.origin[0], r.o[1] = p.frame.origin[1], r.o[2] = p.frame.origin[2];
-                if (inside) {
-                    primary_dir(__ldg(p.xs + col), __ldg(p.ys + row), r.d);
-                }
-                if (MODE == kModePrimary) {
-                    valid = inside;
-                    r.clip = kInfinity;
-                } else {
-                    r.flags = DODRT_RAY_ANY;
-                    if (inside) {
-                        const float4 ph = reinterpret_cast<const float4 *>(p.hits)[slot];
-                        if (__float_as_uint(ph.y) != DODRT_MISS) {
-                            float so[3], sd[3];
-                            shadow_ray(r.o, r.d, ph.x, p.light, so, sd, r.clip);
-                            r.o[0] = so[0], r.o[1] = so[1], r.o[2] = so[2];
-                            r.d[0] = sd[0], r.d[1] = sd[1], r.d[2] = sd[2];
-                            valid = true;
-                        }
-                    }
-                }
-            }
-            const bool rayAny = (r.flags & DODRT_RAY_ANY) != 0u;
-            const float rayClip0 = r.clip;
-            Hit h;
-            h.t = r.clip, h.prim = DODRT_MISS, h.u = h.v = 0.0f;
-            bool aFound = false, decided = !valid;
-            if (valid) {
-                decided = analytic_chain(s, p.classes, r.o, r.d, rayAny, r.clip, h, aFound);
-            }
-            bool survive = false;
-            if (!decided && useTree) {
-                const float inv[3] = {1.0f / r.d[0], 1.0f / r.d[1], 1.0f / r.d[2]};
-                survive = slab(s.bmin, s.bmax, r.o, inv, r.clip, r.tmin, r.tmax) && !(r.tmin > r.clip);
-            }
-            if (writes && !survive) { // finished without the kd-tree
-                const bool blocked = (MODE == kModeShadow) ? (!valid || aFound) : aFound;
-                write_result<MODE>(p, slot, rayAny, rayClip0, h, blocked);
-            }
+            const bool survive = stage_a<MODE>(p, useTree, base + lane, r);
             const unsigned surviveMask = __ballot_sync(0xffffffffu, survive);
             if (survive) {
-                r.hitT = h.t;
-                r.hitPrim = h.prim;
-                r.out = (uint32_t)slot;
-                r.flags |= (uint32_t)(slot >> 32) << 1;
                 pool_store(pool + (poolCount + __popc(surviveMask & ltMask)) * kPoolWords, r);
             }
             poolCount += __popc(surviveMask);
