@@ -217,7 +217,8 @@ def main():
     tmpdir = tempfile.mkdtemp(prefix=f"dodrt_bench_{rank}_")
     mesh_files = workloads.write_mesh_files(w, tmpdir)
     t0 = time.perf_counter()
-    hs = workloads.build_host_scene(w, mesh_files)
+    # GPU arm: lanes stay in creation order, Triangle::reorderLanesByIndices runs on the GPU at upload (f-4)
+    hs = workloads.build_host_scene(w, mesh_files, keep_creation_order=(args.impl != "reference"))
     build_s = time.perf_counter() - t0
 
     if args.impl == "reference":

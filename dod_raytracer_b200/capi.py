@@ -30,7 +30,8 @@ RAY_ANY = 1
 
 EXPORTED_SYMBOLS = [
     "dodrt_abi_version", "dodrt_last_error", "dodrt_device_count",
-    "dodrt_scene_create", "dodrt_scene_destroy", "dodrt_scene_set_kdtree", "dodrt_scene_set_spheres",
+    "dodrt_scene_create", "dodrt_scene_destroy", "dodrt_scene_set_kdtree", "dodrt_scene_set_kdtree_indexed",
+    "dodrt_scene_set_shading_indexed", "dodrt_scene_set_spheres",
     "dodrt_scene_set_planes", "dodrt_scene_set_cylinders", "dodrt_scene_set_boxes", "dodrt_scene_set_epsilon",
     "dodrt_scene_set_kernel_variant", "dodrt_scene_set_shading", "dodrt_render",
     "dodrt_intersect", "dodrt_trace_primary", "dodrt_trace_shadow", "dodrt_trace_frame",

@@ -291,6 +291,7 @@ int dodrt_scene_create(int device, dodrt_scene **scene)
     if (!s) return fail(DODRT_E_NOMEM, "out of host memory");
     s->device = device;
     s->dev.epsilon = 0.0001f; // Config::Epsilon default, config.h:9
+    s->dev.negzero2 = 0x8000000080000000ull;
     {
         const char *t = std::getenv("DODRT_TUNE"); // "num,den,maxNodeRun" (exploration knob)
         unsigned a = 3, b = 1, c = 0xFFFFFFFFu; // measured best on dragon4k (profiles/r01_vote_rule_sweep.txt)
@@ -341,12 +342,22 @@ int dodrt_scene_destroy(dodrt_scene *s)
     return DODRT_OK;
 }
 
-int dodrt_scene_set_kdtree(dodrt_scene *s, const uint64_t *nodes, uint32_t num_nodes, const float *tri_lanes,
-                           uint32_t num_tri_lanes, const float bounds[6])
+// Shared body of dodrt_scene_set_kdtree (prim_nums == nullptr: `tri_lanes` holds num_tri_lanes re-ordered lanes) and
+// dodrt_scene_set_kdtree_indexed (`tri_lanes` holds num_src_lanes lanes in creation order and lane i of the tree is
+// tri_lanes[prim_nums[i]]: Triangle::reorderLanesByIndices, triangle.cpp:349-367, done by the repack kernel's gather).
+static int setKdtree(dodrt_scene *s, const uint64_t *nodes, uint32_t num_nodes, const float *tri_lanes, uint32_t num_src_lanes,
+                     const uint32_t *prim_nums, uint32_t num_tri_lanes, const float bounds[6])
 {
     if (!s) return fail(DODRT_E_INVALID, "scene is NULL");
     if ((num_nodes && !nodes) || (num_tri_lanes && !tri_lanes) || !bounds) {
         return fail(DODRT_E_INVALID, "NULL array with non-zero count");
+    }
+    if (prim_nums) {
+        for (uint32_t i = 0; i < num_tri_lanes; i++) {
+            if (prim_nums[i] >= num_src_lanes) {
+                return fail(DODRT_E_INVALID, "prim_nums[%u] = %u out of range (%u lanes)", i, prim_nums[i], num_src_lanes);
+            }
+        }
     }
     if ((uint64_t)num_tri_lanes * kLane >= (1ull << DODRT_KIND_SHIFT)) {
         return fail(DODRT_E_LIMIT, "%u lanes exceed the %u-bit triangle id space", num_tri_lanes, DODRT_KIND_SHIFT);
@@ -374,14 +385,21 @@ int dodrt_scene_set_kdtree(dodrt_scene *s, const uint64_t *nodes, uint32_t num_n
     }
     if (num_tri_lanes) {
         float *d_lanes = nullptr;
+        uint32_t *d_prim = nullptr;
         const size_t laneBytes = (size_t)num_tri_lanes * 288;
-        CUDA_TRY(cudaMalloc(&d_lanes, laneBytes));
-        cudaError_t e = cudaMemcpy(d_lanes, tri_lanes, laneBytes, cudaMemcpyHostToDevice);
+        const size_t srcBytes = (size_t)(prim_nums ? num_src_lanes : num_tri_lanes) * 288;
+        CUDA_TRY(cudaMalloc(&d_lanes, srcBytes));
+        cudaError_t e = cudaMemcpy(d_lanes, tri_lanes, srcBytes, cudaMemcpyHostToDevice);
+        if (e == cudaSuccess && prim_nums) e = cudaMalloc(&d_prim, (size_t)num_tri_lanes * sizeof(uint32_t));
+        if (e == cudaSuccess && prim_nums) {
+            e = cudaMemcpy(d_prim, prim_nums, (size_t)num_tri_lanes * sizeof(uint32_t), cudaMemcpyHostToDevice);
+        }
         if (e == cudaSuccess) e = cudaMalloc(&s->d_tris, (size_t)num_tri_lanes * kLane * 3 * sizeof(float4));
         if (e == cudaSuccess) e = cudaMalloc(&s->d_lanes4, laneBytes);
-        if (e == cudaSuccess) e = launch_repack_triangles(d_lanes, num_tri_lanes, s->d_tris, s->d_lanes4, nullptr);
+        if (e == cudaSuccess) e = launch_repack_triangles(d_lanes, d_prim, num_tri_lanes, s->d_tris, s->d_lanes4, nullptr);
         if (e == cudaSuccess) e = cudaDeviceSynchronize();
         cudaFree(d_lanes);
+        cudaFree(d_prim);
         if (e != cudaSuccess) return fail(DODRT_E_CUDA, "triangle upload: %s", cudaGetErrorString(e));
         s->launches.fetch_add(1);
     }
@@ -396,6 +414,20 @@ int dodrt_scene_set_kdtree(dodrt_scene *s, const uint64_t *nodes, uint32_t num_n
     }
     s->treeDepth = depth;
     return DODRT_OK;
+}
+
+int dodrt_scene_set_kdtree(dodrt_scene *s, const uint64_t *nodes, uint32_t num_nodes, const float *tri_lanes,
+                           uint32_t num_tri_lanes, const float bounds[6])
+{
+    return setKdtree(s, nodes, num_nodes, tri_lanes, num_tri_lanes, nullptr, num_tri_lanes, bounds);
+}
+
+int dodrt_scene_set_kdtree_indexed(dodrt_scene *s, const uint64_t *nodes, uint32_t num_nodes, const float *tri_lanes,
+                                   uint32_t num_src_lanes, const uint32_t *prim_nums, uint32_t num_tri_lanes,
+                                   const float bounds[6])
+{
+    if (num_tri_lanes && !prim_nums) return fail(DODRT_E_INVALID, "prim_nums is NULL");
+    return setKdtree(s, nodes, num_nodes, tri_lanes, num_src_lanes, prim_nums, num_tri_lanes, bounds);
 }
 
 static int uploadLanes(dodrt_scene *s, float **slot, const float **view, uint32_t *countField, const float *lanes,
@@ -505,8 +537,9 @@ int dodrt_scene_set_cylinders(dodrt_scene *s, const dodrt_cylinder *cylinders, u
     return DODRT_OK;
 }
 
-int dodrt_scene_set_shading(dodrt_scene *s, const void *tri_attributes, uint32_t num_tri_lanes, const float *mesh_colors,
-                            uint32_t num_meshes, const float *sphere_colors, const float *plane_colors)
+static int setShading(dodrt_scene *s, const void *tri_attributes, uint32_t num_src_lanes, const uint32_t *prim_nums,
+                      uint32_t num_tri_lanes, const float *mesh_colors, uint32_t num_meshes, const float *sphere_colors,
+                      const float *plane_colors)
 {
     if (!s) return fail(DODRT_E_INVALID, "scene is NULL");
     if (num_tri_lanes != s->dev.num_tri_lanes) {
@@ -516,9 +549,16 @@ int dodrt_scene_set_shading(dodrt_scene *s, const void *tri_attributes, uint32_t
     if ((s->dev.num_spheres && !sphere_colors) || (s->dev.num_planes && !plane_colors)) {
         return fail(DODRT_E_INVALID, "NULL sphere/plane colours");
     }
+    if (prim_nums) {
+        for (uint32_t i = 0; i < num_tri_lanes; i++) {
+            if (prim_nums[i] >= num_src_lanes) {
+                return fail(DODRT_E_INVALID, "prim_nums[%u] = %u out of range (%u lanes)", i, prim_nums[i], num_src_lanes);
+            }
+        }
+    }
     if (num_tri_lanes) { // every meshAttrIdx must address a mesh colour
         const uint32_t *a = static_cast<const uint32_t *>(tri_attributes);
-        for (uint32_t lane = 0; lane < num_tri_lanes; lane++) {
+        for (uint32_t lane = 0; lane < num_src_lanes; lane++) {
             for (int j = 0; j < kLane; j++) {
                 if (a[(size_t)lane * 80 + j] >= num_meshes) {
                     return fail(DODRT_E_INVALID, "meshAttrIdx %u of lane %u out of range (%u meshes)",
@@ -539,7 +579,20 @@ int dodrt_scene_set_shading(dodrt_scene *s, const void *tri_attributes, uint32_t
         cudaError_t e = cudaMalloc(dst, bytes);
         return e == cudaSuccess ? cudaMemcpy(*dst, src, bytes, cudaMemcpyHostToDevice) : e;
     };
-    CUDA_TRY(upload(&s->d_triAttrs, tri_attributes, (size_t)num_tri_lanes * 320));
+    if (prim_nums && num_tri_lanes) { // Triangle::reorderLanesByIndices (triangle.cpp:358-364) for the attributes, on the GPU
+        uint32_t *d_src = nullptr, *d_prim = nullptr;
+        cudaError_t e = upload(&d_src, tri_attributes, (size_t)num_src_lanes * 320);
+        if (e == cudaSuccess) e = upload(&d_prim, prim_nums, (size_t)num_tri_lanes * sizeof(uint32_t));
+        if (e == cudaSuccess) e = cudaMalloc(&s->d_triAttrs, (size_t)num_tri_lanes * 320);
+        if (e == cudaSuccess) e = launch_gather_lanes(d_src, d_prim, num_tri_lanes, 80, s->d_triAttrs, nullptr);
+        if (e == cudaSuccess) e = cudaDeviceSynchronize();
+        cudaFree(d_src);
+        cudaFree(d_prim);
+        if (e != cudaSuccess) return fail(DODRT_E_CUDA, "attribute upload: %s", cudaGetErrorString(e));
+        s->launches.fetch_add(1);
+    } else {
+        CUDA_TRY(upload(&s->d_triAttrs, tri_attributes, (size_t)num_tri_lanes * 320));
+    }
     CUDA_TRY(upload(&s->d_meshColors, mesh_colors, (size_t)num_meshes * 12));
     CUDA_TRY(upload(&s->d_sphereColors, sphere_colors, (size_t)s->dev.num_spheres * 12));
     CUDA_TRY(upload(&s->d_planeColors, plane_colors, (size_t)s->dev.num_planes * 12));
@@ -548,6 +601,22 @@ int dodrt_scene_set_shading(dodrt_scene *s, const void *tri_attributes, uint32_t
     s->dev.sphere_colors = s->d_sphereColors;
     s->dev.plane_colors = s->d_planeColors;
     return DODRT_OK;
+}
+
+int dodrt_scene_set_shading(dodrt_scene *s, const void *tri_attributes, uint32_t num_tri_lanes, const float *mesh_colors,
+                            uint32_t num_meshes, const float *sphere_colors, const float *plane_colors)
+{
+    return setShading(s, tri_attributes, num_tri_lanes, nullptr, num_tri_lanes, mesh_colors, num_meshes, sphere_colors,
+                      plane_colors);
+}
+
+int dodrt_scene_set_shading_indexed(dodrt_scene *s, const void *tri_attributes, uint32_t num_src_lanes,
+                                    const uint32_t *prim_nums, uint32_t num_tri_lanes, const float *mesh_colors,
+                                    uint32_t num_meshes, const float *sphere_colors, const float *plane_colors)
+{
+    if (num_tri_lanes && !prim_nums) return fail(DODRT_E_INVALID, "prim_nums is NULL");
+    return setShading(s, tri_attributes, num_src_lanes, prim_nums, num_tri_lanes, mesh_colors, num_meshes, sphere_colors,
+                      plane_colors);
 }
 
 int dodrt_scene_set_kernel_variant(dodrt_scene *s, int variant)

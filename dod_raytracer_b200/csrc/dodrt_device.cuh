@@ -56,6 +56,8 @@ struct DeviceScene {
     // traversal scheduling knobs (dodrt_kernels.cu): leaf phase runs when nLeaf*tune[1] >= nNode*tune[0], or after
     // tune[2] consecutive node phases
     uint32_t tune[4];
+    // (-0.0f, -0.0f): the addend that turns FFMA2 into an un-fusable packed multiply (see f2_mul)
+    unsigned long long negzero2;
 };
 
 struct Hit {
@@ -233,6 +235,121 @@ __device__ __forceinline__ bool lane_half_test(const float4 *__restrict__ lane, 
     const bool m1 = triangle_may_hit(Ax.y, Ay.y, Az.y, Bx.y, By.y, Bz.y, Cx.y, Cy.y, Cz.y, o, d);
     const bool m2 = triangle_may_hit(Ax.z, Ay.z, Az.z, Bx.z, By.z, Bz.z, Cx.z, Cy.z, Cz.z, o, d);
     const bool m3 = triangle_may_hit(Ax.w, Ay.w, Az.w, Bx.w, By.w, Bz.w, Cx.w, Cy.w, Cz.w, o, d);
+    if (!(m0 | m1 | m2 | m3)) {
+        return false;
+    }
+    bool any = false;
+    float t, u, v;
+#define DODRT_SLOT(k, M, c)                                                                                        \
+    if (M && triangle_test_fast(make_float4(Ax.c, Ay.c, Az.c, Bx.c), make_float4(By.c, Bz.c, Cx.c, Cy.c),          \
+                                make_float4(Cz.c, 0.0f, 0.0f, 0.0f), o, d, clip, t, u, v)) {                        \
+        clip = t;                                                                                                  \
+        hit.t = t;                                                                                                 \
+        hit.prim = (DODRT_KIND_TRIANGLE << DODRT_KIND_SHIFT) | (firstId + k);                                      \
+        hit.u = u;                                                                                                 \
+        hit.v = v;                                                                                                 \
+        any = true;                                                                                                \
+    }
+    DODRT_SLOT(0, m0, x)
+    DODRT_SLOT(1, m1, y)
+    DODRT_SLOT(2, m2, z)
+    DODRT_SLOT(3, m3, w)
+#undef DODRT_SLOT
+    return any;
+}
+
+// ---- packed fp32 pairs: sm_100a FMUL2 / FADD2 / FFMA2 ------------------------------------------------------------
+// One issue slot does the SAME IEEE operation on two independent fp32 values held in a 64-bit register pair
+// (PTX add/sub/fma .rn.f32x2).  Each half is rounded exactly like the scalar mul.rn / add.rn, so results are
+// bit-identical to the scalar code -- PROVIDED ptxas does not contract a packed multiply with the add that
+// consumes it: ptxas 12.9 fuses mul.rn.f32x2 + add.rn.f32x2 into FFMA2 even with --fmad=false (it honours .rn only
+// for the scalar forms), and it also folds fma(a, b, -0.0) back into a multiply when the -0.0 is a literal.  The
+// multiply is therefore written as fma.rn.f32x2(a, b, nz) with nz = (-0.0f, -0.0f) read from a kernel parameter
+// (DeviceScene::negzero2), which ptxas cannot see through: fl(a*b + (-0)) == fl(a*b) for every input (the sum of
+// an exact product and -0 keeps the product's sign, also for +-0, and inf/NaN propagate alike), and an FFMA2
+// cannot be fused into the FADD2 that follows.  tests/test_sass_audit.py checks the compiled SASS: every FFMA2
+// of the trace kernels has the uniform -0.0 pair as its addend.
+typedef unsigned long long f32x2;
+
+__device__ __forceinline__ f32x2 f2_pack(float lo, float hi)
+{
+    f32x2 r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+    return r;
+}
+__device__ __forceinline__ float f2_lo(f32x2 v)
+{
+    float lo, hi;
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+    return lo;
+}
+__device__ __forceinline__ float f2_hi(f32x2 v)
+{
+    float lo, hi;
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+    return hi;
+}
+__device__ __forceinline__ f32x2 f2_add(f32x2 a, f32x2 b)
+{
+    f32x2 r;
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
+__device__ __forceinline__ f32x2 f2_sub(f32x2 a, f32x2 b)
+{
+    f32x2 r;
+    asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
+__device__ __forceinline__ f32x2 f2_mul(f32x2 a, f32x2 b, f32x2 nz)
+{
+    f32x2 r;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(nz));
+    return r;
+}
+// dot3 for two triangles at once, same association as avxDot: (x1*x2 + y1*y2) + z1*z2
+__device__ __forceinline__ f32x2 f2_dot3(f32x2 ax, f32x2 ay, f32x2 az, f32x2 bx, f32x2 by, f32x2 bz, f32x2 nz)
+{
+    return f2_add(f2_add(f2_mul(ax, bx, nz), f2_mul(ay, by, nz)), f2_mul(az, bz, nz));
+}
+
+// triangle_may_hit for TWO triangle slots (the halves of each operand): the reference's det and a = dot(T, pvec),
+// each half bit-identical to the scalar routine above; the comparisons run on the unpacked halves.
+__device__ __forceinline__ void triangle_may_hit2(f32x2 Ax, f32x2 Ay, f32x2 Az, f32x2 ABx, f32x2 ABy, f32x2 ABz, f32x2 ACx,
+                                                  f32x2 ACy, f32x2 ACz, const f32x2 o2[3], const f32x2 d2[3], f32x2 nz,
+                                                  bool &m0, bool &m1)
+{
+    const f32x2 px = f2_sub(f2_mul(d2[1], ACz, nz), f2_mul(d2[2], ACy, nz));
+    const f32x2 py = f2_sub(f2_mul(d2[2], ACx, nz), f2_mul(d2[0], ACz, nz));
+    const f32x2 pz = f2_sub(f2_mul(d2[0], ACy, nz), f2_mul(d2[1], ACx, nz));
+    const f32x2 det = f2_dot3(px, py, pz, ABx, ABy, ABz, nz);
+    const f32x2 tx = f2_sub(o2[0], Ax), ty = f2_sub(o2[1], Ay), tz = f2_sub(o2[2], Az);
+    const f32x2 a = f2_dot3(tx, ty, tz, px, py, pz, nz);
+    const float det0 = f2_lo(det), det1 = f2_hi(det), a0 = f2_lo(a), a1 = f2_hi(a);
+    const float ad0 = fabsf(det0), ad1 = fabsf(det1);
+    m0 = (ad0 > 0.0f) & !sign_differs_or_zero(a0, det0) & !(fabsf(a0) > ad0 * 1.00001f);
+    m1 = (ad1 > 0.0f) & !sign_differs_or_zero(a1, det1) & !(fabsf(a1) > ad1 * 1.00001f);
+}
+
+__device__ __forceinline__ f32x2 f2_from(const float4 &q, int pair)
+{
+    return pair == 0 ? f2_pack(q.x, q.y) : f2_pack(q.z, q.w);
+}
+
+// lane_half_test with the first stage on packed pairs (variant 6): 44 instead of 88 fp32 issue slots per four
+// triangles.  The exact second stage is the scalar one, in slot order.
+__device__ __forceinline__ bool lane_half_test_packed(const float4 *__restrict__ lane, int h, uint32_t firstId,
+                                                      const float o[3], const float d[3], const f32x2 o2[3],
+                                                      const f32x2 d2[3], f32x2 nz, float &clip, Hit &hit)
+{
+    const float4 Ax = __ldg(lane + 0 + h), Ay = __ldg(lane + 2 + h), Az = __ldg(lane + 4 + h);
+    const float4 Bx = __ldg(lane + 6 + h), By = __ldg(lane + 8 + h), Bz = __ldg(lane + 10 + h);
+    const float4 Cx = __ldg(lane + 12 + h), Cy = __ldg(lane + 14 + h), Cz = __ldg(lane + 16 + h);
+    bool m0, m1, m2, m3;
+    triangle_may_hit2(f2_from(Ax, 0), f2_from(Ay, 0), f2_from(Az, 0), f2_from(Bx, 0), f2_from(By, 0), f2_from(Bz, 0),
+                      f2_from(Cx, 0), f2_from(Cy, 0), f2_from(Cz, 0), o2, d2, nz, m0, m1);
+    triangle_may_hit2(f2_from(Ax, 1), f2_from(Ay, 1), f2_from(Az, 1), f2_from(Bx, 1), f2_from(By, 1), f2_from(Bz, 1),
+                      f2_from(Cx, 1), f2_from(Cy, 1), f2_from(Cz, 1), o2, d2, nz, m2, m3);
     if (!(m0 | m1 | m2 | m3)) {
         return false;
     }

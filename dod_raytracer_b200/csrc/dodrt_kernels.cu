@@ -21,6 +21,9 @@
 //   4  variant 3 plus warp-level regrouping: analytic classes + bounds test for 32 fresh rays at a time, the
 //      survivors compacted (ballot/popc) into a per-warp pool in shared memory from which idle lanes are
 //      refilled (dodrt_pool_kernel.inl).
+//   5  variant 3 plus a cooperative leaf step for stragglers (<= 4 rays waiting: 8/16/32 lanes per ray).
+//   6  variant 3 with the branch-free first stage on packed fp32 pairs (FMUL2/FADD2/FFMA2, dodrt_device.cuh): half
+//      the fp32 issue slots for the same bits.
 // Every variant computes identical results (parity tests run all of them).
 #include "dodrt_kernels.cuh"
 #include "dodrt_prim_bvh.cuh"
@@ -150,12 +153,18 @@ __device__ __forceinline__ void tree_pop(TreeState &st, const uint32_t *stackNod
 }
 
 // One triangle lane (8 consecutive slots, triangle.cpp:43-140) of the leaf this ray is in.
-template <bool SOA>
+template <bool SOA, bool PACKED>
 __device__ __forceinline__ void leaf_step(const DeviceScene &s, TreeState &st, const float o[3], const float d[3], bool any,
                                           float &clip, Hit &hit, bool &found, const uint32_t *stackNode,
                                           const float *stackTmin, const float *stackTmax)
 {
-    if (SOA) {
+    if (PACKED) {
+        const float4 *lane = s.lanes4 + (size_t)(st.triCur >> 3) * 18;
+        const f32x2 o2[3] = {f2_pack(o[0], o[0]), f2_pack(o[1], o[1]), f2_pack(o[2], o[2])};
+        const f32x2 d2[3] = {f2_pack(d[0], d[0]), f2_pack(d[1], d[1]), f2_pack(d[2], d[2])};
+        if (lane_half_test_packed(lane, 0, st.triCur, o, d, o2, d2, s.negzero2, clip, hit)) found = true;
+        if (!(any && found) && lane_half_test_packed(lane, 1, st.triCur + 4, o, d, o2, d2, s.negzero2, clip, hit)) found = true;
+    } else if (SOA) {
         const float4 *lane = s.lanes4 + (size_t)(st.triCur >> 3) * 18;
         if (lane_half_test(lane, 0, st.triCur, o, d, clip, hit)) found = true;
         if (!(any && found) && lane_half_test(lane, 1, st.triCur + 4, o, d, clip, hit)) found = true;
@@ -314,7 +323,7 @@ __device__ __forceinline__ void leaf_step_coop(const DeviceScene &s, TreeState &
     }
 }
 
-template <bool SOA, bool SHARE>
+template <bool SOA, bool SHARE, bool PACKED>
 __device__ __forceinline__ bool kdtree_query_voted(const DeviceScene &s, bool enter, const float o[3], const float d[3],
                                                    bool any, float &clip, Hit &hit)
 {
@@ -340,7 +349,7 @@ __device__ __forceinline__ bool kdtree_query_voted(const DeviceScene &s, bool en
                 leaf_step_coop(s, st, leafMask, nLeaf, wantLeaf, o, d, any, clip, hit, found, stackNode, stackTmin,
                                stackTmax);
             } else if (wantLeaf) {
-                leaf_step<SOA>(s, st, o, d, any, clip, hit, found, stackNode, stackTmin, stackTmax);
+                leaf_step<SOA, PACKED>(s, st, o, d, any, clip, hit, found, stackNode, stackTmin, stackTmax);
             }
         } else {
             ++nodeRun;
@@ -406,7 +415,7 @@ __device__ __forceinline__ bool query(const DeviceScene &s, uint32_t classes, bo
     const bool enter = !decided && (classes & DODRT_CLS_TREE);
     Hit h;
     if (VARIANT >= 2) {
-        if (kdtree_query_voted<VARIANT >= 3, VARIANT == 5>(s, enter, o, d, any, clip, h)) {
+        if (kdtree_query_voted<VARIANT >= 3, VARIANT == 5, VARIANT == 6>(s, enter, o, d, any, clip, h)) {
             hit = h;
             found = true;
         }
@@ -592,14 +601,17 @@ template <int MODE, int VARIANT> __global__ void __launch_bounds__(128, DODRT_MI
 #include "dodrt_pool_kernel.inl"
 
 // One thread per triangle slot: gather the 9 SoA floats of slot j of lane i and emit A, AB, AC.
-__global__ void repack_triangles_kernel(const float *__restrict__ lanes, uint32_t numLanes, float4 *__restrict__ tris,
-                                        float *__restrict__ lanes4)
+// `primNums` (optional) = KDTree::m_primNums: output lane i is source lane primNums[i] -- the reference's
+// Triangle::reorderLanesByIndices (triangle.cpp:349-367) fused into the upload (dodrt_scene_set_kdtree_indexed).
+__global__ void repack_triangles_kernel(const float *__restrict__ lanes, const uint32_t *__restrict__ primNums,
+                                        uint32_t numLanes, float4 *__restrict__ tris, float *__restrict__ lanes4)
 {
     const uint64_t idx = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= (uint64_t)numLanes * kLane) {
         return;
     }
-    const float *lane = lanes + (idx / kLane) * 72;
+    const uint64_t srcLane = primNums ? (uint64_t)__ldg(primNums + idx / kLane) : idx / kLane;
+    const float *lane = lanes + srcLane * 72;
     const uint32_t j = (uint32_t)(idx % kLane);
     const float Ax = lane[0 * kLane + j], Ay = lane[1 * kLane + j], Az = lane[2 * kLane + j];
     const float Bx = lane[3 * kLane + j], By = lane[4 * kLane + j], Bz = lane[5 * kLane + j];
@@ -618,6 +630,18 @@ __global__ void repack_triangles_kernel(const float *__restrict__ lanes, uint32_
     out[6 * kLane] = Cx - Ax;
     out[7 * kLane] = Cy - Ay;
     out[8 * kLane] = Cz - Az;
+}
+
+// out[lane][w] = in[primNums[lane]][w]: the lane re-order for any per-lane record of `wordsPerLane` 32-bit words
+__global__ void gather_lanes_kernel(const uint32_t *__restrict__ in, const uint32_t *__restrict__ primNums, uint32_t numLanes,
+                                    uint32_t wordsPerLane, uint32_t *__restrict__ out)
+{
+    const uint64_t idx = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= (uint64_t)numLanes * wordsPerLane) {
+        return;
+    }
+    const uint64_t lane = idx / wordsPerLane, w = idx % wordsPerLane;
+    out[idx] = in[(uint64_t)__ldg(primNums + lane) * wordsPerLane + w];
 }
 
 // Inverse of slot_to_pixel over all ranks: pixel -> (rank, slot).  Pure data movement (16+1 B per pixel).
@@ -713,7 +737,8 @@ cudaError_t trace_launch_config(int device, TraceMode mode, int variant, LaunchC
     case 2: return config_mode<2>(device, mode, cfg);
     case 3: return config_mode<3>(device, mode, cfg);
     case 4: return config_mode<4>(device, mode, cfg);
-    default: return config_mode<5>(device, mode, cfg);
+    case 5: return config_mode<5>(device, mode, cfg);
+    default: return config_mode<6>(device, mode, cfg);
     }
 }
 
@@ -735,7 +760,8 @@ cudaError_t launch_trace(TraceMode mode, const TraceParams &p, const LaunchConfi
     case 2: launch_mode<2>(mode, p, cfg, stream); break;
     case 3: launch_mode<3>(mode, p, cfg, stream); break;
     case 4: launch_mode<4>(mode, p, cfg, stream); break;
-    default: launch_mode<5>(mode, p, cfg, stream); break;
+    case 5: launch_mode<5>(mode, p, cfg, stream); break;
+    default: launch_mode<6>(mode, p, cfg, stream); break;
     }
     return cudaGetLastError();
 }
@@ -752,14 +778,26 @@ cudaError_t launch_assemble(const dodrt_frame &frame, uint32_t tiles_x, const do
     return cudaGetLastError();
 }
 
-cudaError_t launch_repack_triangles(const float *d_lanes, uint32_t num_lanes, float4 *d_tris, float4 *d_lanes4,
-                                    cudaStream_t stream)
+cudaError_t launch_gather_lanes(const uint32_t *d_in, const uint32_t *d_prim_nums, uint32_t num_lanes, uint32_t words_per_lane,
+                                uint32_t *d_out, cudaStream_t stream)
+{
+    const uint64_t n = (uint64_t)num_lanes * words_per_lane;
+    if (n == 0) return cudaSuccess;
+    const int block = 256;
+    gather_lanes_kernel<<<(unsigned)((n + block - 1) / block), block, 0, stream>>>(d_in, d_prim_nums, num_lanes, words_per_lane,
+                                                                                    d_out);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_repack_triangles(const float *d_lanes, const uint32_t *d_prim_nums, uint32_t num_lanes, float4 *d_tris,
+                                    float4 *d_lanes4, cudaStream_t stream)
 {
     const uint64_t n = (uint64_t)num_lanes * kLane;
     if (n == 0) return cudaSuccess;
     const int block = 256;
     const unsigned grid = (unsigned)((n + block - 1) / block);
-    repack_triangles_kernel<<<grid, block, 0, stream>>>(d_lanes, num_lanes, d_tris, reinterpret_cast<float *>(d_lanes4));
+    repack_triangles_kernel<<<grid, block, 0, stream>>>(d_lanes, d_prim_nums, num_lanes, d_tris,
+                                                        reinterpret_cast<float *>(d_lanes4));
     return cudaGetLastError();
 }
 

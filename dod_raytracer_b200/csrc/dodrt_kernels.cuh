@@ -12,7 +12,7 @@ enum TraceMode : int {
 };
 constexpr int kNumModes = 4;
 
-constexpr int kNumVariants = 6;    // see the header comment of dodrt_kernels.cu
+constexpr int kNumVariants = 7;    // see the header comment of dodrt_kernels.cu
 constexpr int kDefaultVariant = 3;
 int default_variant();             // kDefaultVariant unless env DODRT_VARIANT overrides it
 
@@ -77,7 +77,11 @@ cudaError_t launch_assemble(const dodrt_frame &frame, uint32_t tiles_x, const do
                             cudaStream_t stream);
 
 // Upload helper: reference lanes (288 B, SoA of 8) -> per-triangle 48-B records with AB/AC.
-cudaError_t launch_repack_triangles(const float *d_lanes, uint32_t num_lanes, float4 *d_tris, float4 *d_lanes4,
-                                    cudaStream_t stream);
+// `d_prim_nums` (optional): output lane i = source lane d_prim_nums[i] (Triangle::reorderLanesByIndices fused in).
+cudaError_t launch_repack_triangles(const float *d_lanes, const uint32_t *d_prim_nums, uint32_t num_lanes, float4 *d_tris,
+                                    float4 *d_lanes4, cudaStream_t stream);
+// generic per-lane gather (shading attributes): out[i] = in[d_prim_nums[i]], `words_per_lane` 32-bit words each
+cudaError_t launch_gather_lanes(const uint32_t *d_in, const uint32_t *d_prim_nums, uint32_t num_lanes, uint32_t words_per_lane,
+                                uint32_t *d_out, cudaStream_t stream);
 
 } // namespace dodrt

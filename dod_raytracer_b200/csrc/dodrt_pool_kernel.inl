@@ -233,7 +233,7 @@ template <int MODE> __global__ void __launch_bounds__(32 * kWarpsPerBlock) trace
             }
             if (__popc(leafMask) >= __popc(nodeMask)) {
                 if (wantLeaf) {
-                    leaf_step<true>(s, st, o, d, any, clip, hit, found, stackNode, stackTmin, stackTmax);
+                    leaf_step<true, false>(s, st, o, d, any, clip, hit, found, stackNode, stackTmin, stackTmax);
                 }
             } else if (wantNode) {
                 node_step(s, st, o, d, clip, stackNode, stackTmin, stackTmax);

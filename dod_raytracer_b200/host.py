@@ -16,6 +16,7 @@ from . import capi
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "lib", "libdodrt_host.so")
+BUILD_KEEP_CREATION_ORDER = 1  # DODRT_HOST_BUILD_KEEP_CREATION_ORDER (include/dodrt_host.h)
 
 
 class Config(C.Structure):
@@ -153,9 +154,12 @@ class HostScene:
     def add_analytic_scene(self, seed: int = 4, count: int = 10000):
         _check(self._lib.dodrt_host_add_analytic_scene(self._h, C.c_uint32(seed), C.c_uint32(count)))
 
-    def build_tree(self):
-        """KDTree::buildTree() (kdtree.cpp:252-260) incl. the lane re-order."""
-        _check(self._lib.dodrt_host_build_tree(self._h))
+    def build_tree(self, keep_creation_order: bool = False):
+        """KDTree::buildTree() (kdtree.cpp:252-260).  By default incl. the lane re-order (triangle.cpp:349-367);
+        with `keep_creation_order` the lanes stay as created and `upload` lets the GPU do the re-order
+        (dodrt_scene_set_kdtree_indexed)."""
+        _check(self._lib.dodrt_host_build_tree_ex(self._h, C.c_uint32(BUILD_KEEP_CREATION_ORDER if keep_creation_order else 0)))
+        self._creation_order = bool(keep_creation_order)
 
     # ---- export ---------------------------------------------------------------------------------------
     def sizes(self) -> Sizes:
@@ -163,12 +167,16 @@ class HostScene:
         _check(self._lib.dodrt_host_sizes_get(self._h, C.byref(z)))
         return z
 
-    def arrays(self, normals: bool = False) -> dict:
+    def arrays(self, normals: bool = False, raw: bool = False) -> dict:
+        """Copies of the exported arrays.  After build_tree(keep_creation_order=True) the per-lane arrays are gathered
+        through prim_nums here (numpy) so that callers always see the re-ordered scene; `raw` returns them as stored."""
         z = self.sizes()
         L = self._lib
         out = dict(
             nodes=_view(L.dodrt_host_nodes(self._h), (z.num_nodes,), np.uint64),
-            tri_lanes=_view(L.dodrt_host_tri_lanes(self._h), (z.num_lanes, 72), np.float32),
+            # re-ordered lanes, or (build_tree(keep_creation_order=True)) the lanes as created
+            tri_lanes=_view(L.dodrt_host_tri_lanes(self._h),
+                            (z.num_orig_lanes if getattr(self, "_creation_order", False) else z.num_lanes, 72), np.float32),
             prim_nums=_view(L.dodrt_host_prim_nums(self._h), (z.num_lanes if z.num_nodes else 0,), np.uint32),
             bounds=_view(L.dodrt_host_bounds(self._h), (6,), np.float32),
             sphere_lanes=_view(L.dodrt_host_sphere_lanes(self._h), ((z.num_spheres + 7) // 8, 4, 8), np.float32),
@@ -182,9 +190,16 @@ class HostScene:
             num_triangles=z.num_triangles,
         )
         if normals:
-            out["tri_normals"] = _view(L.dodrt_host_tri_normals(self._h), (z.num_lanes * 8, 9), np.float32)
-            out["tri_attributes"] = _view(L.dodrt_host_tri_attributes(self._h), (z.num_lanes, 80), np.uint32)
+            nl = z.num_orig_lanes if getattr(self, "_creation_order", False) else z.num_lanes
+            out["tri_normals"] = _view(L.dodrt_host_tri_normals(self._h), (nl * 8, 9), np.float32)
+            out["tri_attributes"] = _view(L.dodrt_host_tri_attributes(self._h), (nl, 80), np.uint32)
             out["mesh_colors"] = _view(L.dodrt_host_mesh_colors(self._h), (L.dodrt_host_num_meshes(self._h), 3), np.float32)
+        if getattr(self, "_creation_order", False) and not raw and z.num_nodes:
+            pn = out["prim_nums"]
+            out["tri_lanes"] = out["tri_lanes"][pn]
+            if normals:
+                out["tri_normals"] = out["tri_normals"].reshape(-1, 8, 9)[pn].reshape(-1, 9)
+                out["tri_attributes"] = out["tri_attributes"][pn]
         return out
 
     def upload(self, device: int = 0, shading: bool = False) -> capi.Scene:
@@ -194,7 +209,13 @@ class HostScene:
         L = self._lib
         g = capi.Scene(device)
         cl = capi.load()
-        if z.num_nodes:
+        indexed = getattr(self, "_creation_order", False)
+        if z.num_nodes and indexed:
+            capi._check(cl.dodrt_scene_set_kdtree_indexed(
+                g._h, C.c_void_p(L.dodrt_host_nodes(self._h)), C.c_uint32(z.num_nodes),
+                C.c_void_p(L.dodrt_host_tri_lanes(self._h)), C.c_uint32(z.num_orig_lanes),
+                C.c_void_p(L.dodrt_host_prim_nums(self._h)), C.c_uint32(z.num_lanes), C.c_void_p(L.dodrt_host_bounds(self._h))))
+        elif z.num_nodes:
             capi._check(cl.dodrt_scene_set_kdtree(g._h, C.c_void_p(L.dodrt_host_nodes(self._h)), C.c_uint32(z.num_nodes),
                                                   C.c_void_p(L.dodrt_host_tri_lanes(self._h)), C.c_uint32(z.num_lanes),
                                                   C.c_void_p(L.dodrt_host_bounds(self._h))))
@@ -210,7 +231,13 @@ class HostScene:
         if z.num_boxes:
             capi._check(cl.dodrt_scene_set_boxes(g._h, C.c_void_p(L.dodrt_host_box_lanes(self._h)), C.c_uint32(z.num_boxes)))
         g.set_epsilon(float(L.dodrt_host_epsilon(self._h)))
-        if shading:
+        if shading and indexed:
+            capi._check(cl.dodrt_scene_set_shading_indexed(
+                g._h, C.c_void_p(L.dodrt_host_tri_attributes(self._h)), C.c_uint32(z.num_orig_lanes),
+                C.c_void_p(L.dodrt_host_prim_nums(self._h)), C.c_uint32(z.num_lanes),
+                C.c_void_p(L.dodrt_host_mesh_colors(self._h)), C.c_uint32(L.dodrt_host_num_meshes(self._h)),
+                C.c_void_p(L.dodrt_host_sphere_colors(self._h)), C.c_void_p(L.dodrt_host_plane_colors(self._h))))
+        elif shading:
             capi._check(cl.dodrt_scene_set_shading(
                 g._h, C.c_void_p(L.dodrt_host_tri_attributes(self._h)), C.c_uint32(z.num_lanes),
                 C.c_void_p(L.dodrt_host_mesh_colors(self._h)), C.c_uint32(L.dodrt_host_num_meshes(self._h)),

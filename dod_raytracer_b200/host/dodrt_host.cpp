@@ -7,6 +7,8 @@
 #include "../../include/dodrt_host.h"
 
 #include <algorithm>
+#include <atomic>
+#include <chrono>
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
@@ -16,6 +18,8 @@
 #include <limits>
 #include <new>
 #include <string>
+#include <thread>
+#include <type_traits>
 #include <unordered_map>
 #include <vector>
 
@@ -142,6 +146,8 @@ struct dodrt_host_scene {
     Box bounds{{0, 0, 0}, {0, 0, 0}};
     float boundsOut[6] = {0, 0, 0, 0, 0, 0};
     bool built = false;
+    double buildSeconds = 0.0, reorderSeconds = 0.0;
+    bool creationOrder = false; // lanes / normals / attrs were NOT re-ordered (DODRT_HOST_BUILD_KEEP_CREATION_ORDER)
     // analytic shapes
     std::vector<float> sphereLanes, sphereColors;
     uint32_t numSpheres = 0;
@@ -266,15 +272,28 @@ int addMesh(dodrt_host_scene *s, std::vector<Vec3> &pos, const uint32_t *idx, ui
         }
     }
     std::vector<Vec3> nrm;
+    const auto t0 = std::chrono::steady_clock::now();
     smoothNormals(pos, idx, numTris, nrm);
+    const auto t1 = std::chrono::steady_clock::now();
     const float meshColor[3] = {(float)0.1, (float)0.8, (float)0.3}; // mesh.cpp:23
     s->meshColors.insert(s->meshColors.end(), meshColor, meshColor + 3);
-    s->lanes.reserve(s->lanes.size() + numTris / kLane + 1);
-    s->normals.reserve(s->normals.size() + numTris / kLane + 1);
+    // grow geometrically: an exact reserve per mesh re-copies every earlier mesh (quadratic for many instances)
+    const size_t need = s->lanes.size() + numTris / kLane + 1;
+    if (need > s->lanes.capacity()) {
+        const size_t cap = std::max(need, s->lanes.capacity() * 2);
+        s->lanes.reserve(cap);
+        s->normals.reserve(cap);
+        s->attrs.reserve(cap);
+    }
     for (uint32_t f = 0; f < numTris; f++) {
         Vec3 p[3] = {pos[idx[f * 3]], pos[idx[f * 3 + 1]], pos[idx[f * 3 + 2]]};
         Vec3 n[3] = {nrm[idx[f * 3]], nrm[idx[f * 3 + 1]], nrm[idx[f * 3 + 2]]};
         pushTriangle(s, p, n);
+    }
+    if (std::getenv("DODRT_HOST_VERBOSE")) {
+        std::fprintf(stderr, "dodrt_host: add_mesh %u triangles: normals %.3f s, lanes %.3f s\n", numTris,
+                     std::chrono::duration<double>(t1 - t0).count(),
+                     std::chrono::duration<double>(std::chrono::steady_clock::now() - t1).count());
     }
     return DODRT_OK;
 }
@@ -341,9 +360,20 @@ struct Edge { // KDTree::AxisOffsetInEdge, kdtree.cpp:12-29
     bool isEnd;
 };
 
+// The recursion of kdtree.cpp:95-250 is a pure function of (depth, badRefines, node bounds, lane list): it emits the
+// subtree's nodes in DFS pre-order and appends its leaves' lane numbers.  Only two things tie a subtree to its
+// position in the whole tree -- the absolute right-child indices (Node::initInteriorNode) and the absolute
+// m_primNums offsets of its leaves (Node::initLeafNode) -- so subtrees can be built CONCURRENTLY into private
+// buffers with buffer-relative indices and spliced in afterwards, re-based by the splice position.  The result is
+// the reference's tree bit for bit (tests/test_host_vs_ref.py, tests/test_host_parallel_build.py), because every
+// decision inside a subtree (edge sort with libstdc++'s introsort on the same input sequence, the SAH sweep with its
+// unsigned-cost quirk, the partition order) is executed by the same code on the same data.
+// Also: the three edge lists are built and sorted LAZILY, one axis at a time, in the order the sweep visits them
+// (kdtree.cpp:140-200 leaves the loop as soon as an axis found a cost below the leaf cost); the reference sorts all
+// three up front (kdtree.cpp:113-137), which does not influence any value the sweep reads.
 class TreeBuilder {
   public:
-    TreeBuilder(dodrt_host_scene *s) : s_(s) {}
+    TreeBuilder(dodrt_host_scene *s, unsigned threads) : s_(s), maxWorkers_(threads > 1 ? threads - 1 : 0) {}
 
     void run()
     {
@@ -352,6 +382,8 @@ class TreeBuilder {
         s_->maxDepth = (uint32_t)std::round(std::log2(8.0f + (1.3f * numLanes)));
         Box world{{kInf, kInf, kInf}, {-kInf, -kInf, -kInf}};
         std::vector<uint32_t> laneNumbers;
+        laneBoxes_.reserve(numLanes);
+        laneNumbers.reserve(numLanes);
         for (uint32_t i = 0; i < s_->numTriangles; i += kLane) { // kdtree.cpp:84-90
             const uint32_t len = std::min(kLane, s_->numTriangles - i);
             laneBoxes_.push_back(laneBox(i / kLane, len));
@@ -359,12 +391,20 @@ class TreeBuilder {
             laneNumbers.push_back(i / kLane);
         }
         s_->bounds = world;
-        s_->nodes.clear();
-        s_->primNums.clear();
-        build(s_->maxDepth, 0, world, laneNumbers);
+        SubTree root;
+        build(root, s_->maxDepth, 0, world, laneNumbers);
+        s_->nodes.swap(root.nodes);
+        s_->primNums.swap(root.prims);
+        for (int a = 0; a < 3; a++) std::vector<Edge>().swap(scratch()[a]); // this thread's copy; workers' died with them
     }
 
   private:
+    struct SubTree { // nodes with indices relative to this buffer
+        std::vector<uint64_t> nodes;
+        std::vector<uint32_t> prims;
+    };
+    static constexpr size_t kTaskMinLanes = 4096; // smaller subtrees are not worth a thread
+
     Box laneBox(uint32_t lane, uint32_t len) const // Triangle::getBoundingBox, triangle.cpp:294-339
     {
         Box box{{kInf, kInf, kInf}, {-kInf, -kInf, -kInf}};
@@ -384,33 +424,69 @@ class TreeBuilder {
         return box;
     }
 
-    void makeLeaf(const std::vector<uint32_t> &laneNums) // Node::initLeafNode, kdtree.cpp:42-56
+    static void makeLeaf(SubTree &out, const std::vector<uint32_t> &laneNums) // Node::initLeafNode, kdtree.cpp:42-56
     {
         const uint32_t w0 = 3u | ((uint32_t)laneNums.size() << 2);
-        const uint32_t w1 = (uint32_t)s_->primNums.size();
-        s_->nodes.push_back((uint64_t)w0 | ((uint64_t)w1 << 32));
-        s_->primNums.insert(s_->primNums.end(), laneNums.begin(), laneNums.end());
+        const uint32_t w1 = (uint32_t)out.prims.size();
+        out.nodes.push_back((uint64_t)w0 | ((uint64_t)w1 << 32));
+        out.prims.insert(out.prims.end(), laneNums.begin(), laneNums.end());
     }
 
-    void build(unsigned depth, unsigned badRefines, const Box &nodeBounds, std::vector<uint32_t> &laneNums)
+    // append `src` to `dst`, re-basing right-child indices and m_primNums offsets by the splice position
+    static void splice(SubTree &dst, const SubTree &src)
+    {
+        const uint64_t nodeBase = dst.nodes.size(), primBase = dst.prims.size();
+        dst.nodes.reserve(dst.nodes.size() + src.nodes.size());
+        for (uint64_t n : src.nodes) {
+            if ((n & 3u) == 3u) {
+                n += primBase << 32; // leaf: word1 = first entry in m_primNums
+            } else {
+                n += nodeBase << 2; // interior: word0[31:2] = right child index
+            }
+            dst.nodes.push_back(n);
+        }
+        dst.prims.insert(dst.prims.end(), src.prims.begin(), src.prims.end());
+    }
+
+    static std::vector<Edge> *scratch()
+    {
+        thread_local std::vector<Edge> edges[3];
+        return edges;
+    }
+
+    bool acquireWorker()
+    {
+        unsigned cur = workers_.load(std::memory_order_relaxed);
+        while (cur < maxWorkers_) {
+            if (workers_.compare_exchange_weak(cur, cur + 1, std::memory_order_acq_rel)) return true;
+        }
+        return false;
+    }
+
+    void build(SubTree &out, unsigned depth, unsigned badRefines, const Box &nodeBounds, std::vector<uint32_t> &laneNums)
     {
         const dodrt_host_config &cfg = s_->cfg;
         if (depth == 0 || laneNums.size() <= cfg.max_prims) { // kdtree.cpp:106
-            makeLeaf(laneNums);
+            makeLeaf(out, laneNums);
             return;
         }
-        std::vector<Edge> edges[3];
-        for (int a = 0; a < 3; a++) edges[a].reserve(laneNums.size() * 2);
-        for (uint32_t lane : laneNums) { // kdtree.cpp:118-127: Start then End, per lane, per axis
-            const Box &b = laneBoxes_[lane];
-            for (int a = 0; a < 3; a++) {
-                edges[a].push_back(Edge{b.lo[a], lane, false});
-                edges[a].push_back(Edge{b.hi[a], lane, true});
+        // per-thread scratch: the edge lists are dead before the recursion, so one set per thread serves every node
+        std::vector<Edge> *edges = scratch();
+        for (int a = 0; a < 3; a++) edges[a].clear();
+        auto sortedAxis = [&](unsigned a) -> const std::vector<Edge> & {
+            std::vector<Edge> &e = edges[a];
+            if (e.empty()) {
+                e.reserve(laneNums.size() * 2);
+                for (uint32_t lane : laneNums) { // kdtree.cpp:118-127: Start then End, per lane
+                    const Box &b = laneBoxes_[lane];
+                    e.push_back(Edge{b.lo[a], lane, false});
+                    e.push_back(Edge{b.hi[a], lane, true});
+                }
+                // kdtree.cpp:128-137: offset-only comparator (ties: libstdc++ introsort order)
+                std::sort(e.begin(), e.end(), [](const Edge &x, const Edge &y) { return x.offset < y.offset; });
             }
-        }
-        for (int a = 0; a < 3; a++) { // kdtree.cpp:128-137: offset-only comparator (ties: libstdc++ introsort order)
-            std::sort(edges[a].begin(), edges[a].end(), [](const Edge &x, const Edge &y) { return x.offset < y.offset; });
-        }
+            return e;
+        };
 
         // SAH sweep, kdtree.cpp:140-200.  bestSplitCost is an UNSIGNED that receives float costs
         // (truncation on every assignment) -- a reference quirk the tree shape depends on.
@@ -424,7 +500,7 @@ class TreeBuilder {
             const unsigned axis = (maxAxis + i) % 3;
             unsigned numLeft = 0;
             unsigned numRight = (unsigned)laneNums.size();
-            const std::vector<Edge> &ax = edges[axis];
+            const std::vector<Edge> &ax = sortedAxis(axis);
             for (unsigned j = 0; j < ax.size(); j++) {
                 const Edge &e = ax[j];
                 if (e.isEnd) numRight--;
@@ -448,40 +524,95 @@ class TreeBuilder {
         }
         if (bestSplitCost > originalSplitCost) badRefines++; // kdtree.cpp:202
 
-        const size_t nodeIdx = s_->nodes.size();
+        const size_t nodeIdx = out.nodes.size();
         if (bestSplitIdx == UINT32_MAX || badRefines == 3 ||
             (bestSplitCost > 4 * originalSplitCost && laneNums.size() < 16)) { // kdtree.cpp:208-214
-            makeLeaf(laneNums);
+            makeLeaf(out, laneNums);
             return;
         }
-        s_->nodes.push_back(0);
+        out.nodes.push_back(0);
 
         const float splitOffset = edges[splitAxis][bestSplitIdx].offset;
         Box leftBounds = nodeBounds, rightBounds = nodeBounds;
         leftBounds.hi[splitAxis] = splitOffset;
         rightBounds.lo[splitAxis] = splitOffset;
         std::vector<uint32_t> leftLanes, rightLanes; // kdtree.cpp:224-243
-        const std::vector<Edge> &ax = edges[splitAxis];
-        for (unsigned i = 0; i < bestSplitIdx; i++) {
-            if (!ax[i].isEnd) leftLanes.push_back(ax[i].lane);
+        {
+            const std::vector<Edge> &ax = edges[splitAxis];
+            leftLanes.reserve(laneNums.size());
+            rightLanes.reserve(laneNums.size());
+            for (unsigned i = 0; i < bestSplitIdx; i++) {
+                if (!ax[i].isEnd) leftLanes.push_back(ax[i].lane);
+            }
+            for (size_t i = (size_t)bestSplitIdx + 1; i < ax.size(); i++) {
+                if (ax[i].isEnd) rightLanes.push_back(ax[i].lane);
+            }
         }
-        for (size_t i = (size_t)bestSplitIdx + 1; i < ax.size(); i++) {
-            if (ax[i].isEnd) rightLanes.push_back(ax[i].lane);
-        }
-        for (int a = 0; a < 3; a++) std::vector<Edge>().swap(edges[a]); // free before recursing
+        const bool fork = laneNums.size() >= kTaskMinLanes && acquireWorker();
+        std::vector<uint32_t>().swap(laneNums);                          // the caller's copy is dead too
 
-        build(depth - 1, badRefines, leftBounds, leftLanes);
-        // Node::initInteriorNode, kdtree.cpp:58-64: flags = axis, right child = next node index
         uint32_t w1;
         std::memcpy(&w1, &splitOffset, 4);
-        const uint32_t w0 = splitAxis | ((uint32_t)s_->nodes.size() << 2);
-        s_->nodes[nodeIdx] = (uint64_t)w0 | ((uint64_t)w1 << 32);
-        build(depth - 1, badRefines, rightBounds, rightLanes);
+        if (fork) {
+            // left subtree on another thread, right subtree here, both into private buffers; splice in DFS order
+            SubTree leftSub, rightSub;
+            std::thread worker([&] {
+                build(leftSub, depth - 1, badRefines, leftBounds, leftLanes);
+                workers_.fetch_sub(1, std::memory_order_acq_rel);
+            });
+            build(rightSub, depth - 1, badRefines, rightBounds, rightLanes);
+            worker.join();
+            splice(out, leftSub);
+            const uint32_t w0 = splitAxis | ((uint32_t)out.nodes.size() << 2);
+            out.nodes[nodeIdx] = (uint64_t)w0 | ((uint64_t)w1 << 32);
+            splice(out, rightSub);
+            return;
+        }
+        build(out, depth - 1, badRefines, leftBounds, leftLanes);
+        // Node::initInteriorNode, kdtree.cpp:58-64: flags = axis, right child = next node index
+        const uint32_t w0 = splitAxis | ((uint32_t)out.nodes.size() << 2);
+        out.nodes[nodeIdx] = (uint64_t)w0 | ((uint64_t)w1 << 32);
+        build(out, depth - 1, badRefines, rightBounds, rightLanes);
     }
 
     dodrt_host_scene *s_;
     std::vector<Box> laneBoxes_;
+    const unsigned maxWorkers_;
+    std::atomic<unsigned> workers_{0};
 };
+
+// Triangle::reorderLanesByIndices (triangle.cpp:349-367): out[i] = in[primNums[i]], split over `threads` threads
+template <typename T>
+void gatherLanes(const std::vector<T> &in, const std::vector<uint32_t> &primNums, std::vector<T> &out, unsigned threads)
+{
+    static_assert(std::is_trivially_copyable<T>::value, "lane records are plain data");
+    out.resize(primNums.size());
+    const size_t n = primNums.size();
+    threads = (unsigned)std::max<size_t>(1, std::min<size_t>(threads, n / 65536 + 1));
+    std::vector<std::thread> pool;
+    for (unsigned t = 0; t < threads; t++) {
+        const size_t lo = n * t / threads, hi = n * (t + 1) / threads;
+        auto work = [&in, &primNums, &out, lo, hi] {
+            for (size_t i = lo; i < hi; i++) out[i] = in[primNums[i]];
+        };
+        if (t + 1 == threads) {
+            work();
+        } else {
+            pool.emplace_back(work);
+        }
+    }
+    for (std::thread &th : pool) th.join();
+}
+
+unsigned hostThreads()
+{
+    if (const char *e = std::getenv("DODRT_HOST_THREADS")) {
+        const int v = std::atoi(e);
+        if (v >= 1) return (unsigned)v;
+    }
+    const unsigned hw = std::thread::hardware_concurrency();
+    return hw ? hw : 1;
+}
 
 void appendLane(std::vector<float> &lanes, uint32_t index, uint32_t floatsPerLane, const float *values, uint32_t numValues)
 {
@@ -719,27 +850,38 @@ int dodrt_host_add_analytic_scene(dodrt_host_scene *s, uint32_t seed, uint32_t c
     return DODRT_OK;
 }
 
-int dodrt_host_build_tree(dodrt_host_scene *s)
+int dodrt_host_build_tree_ex(dodrt_host_scene *s, uint32_t flags)
 {
     if (!s) return fail("NULL argument");
     if (s->built) return fail("tree already built");
+    if (flags & ~(uint32_t)DODRT_HOST_BUILD_KEEP_CREATION_ORDER) return fail("unknown build flags 0x%x", flags);
+    const unsigned threads = hostThreads();
     s->numOrigLanes = (uint32_t)s->lanes.size();
-    TreeBuilder(s).run();
-    // Triangle::reorderLanesByIndices, triangle.cpp:349-367
-    std::vector<TriLane> lanes;
-    std::vector<NormalLane> normals;
-    std::vector<AttrLane> attrs;
-    lanes.reserve(s->primNums.size());
-    normals.reserve(s->primNums.size());
-    attrs.reserve(s->primNums.size());
-    for (uint32_t idx : s->primNums) {
-        lanes.push_back(s->lanes[idx]);
-        normals.push_back(s->normals[idx]);
-        attrs.push_back(s->attrs[idx]);
+    const auto t0 = std::chrono::steady_clock::now();
+    TreeBuilder tb(s, threads);
+    tb.run();
+    const auto t1 = std::chrono::steady_clock::now();
+    if (!(flags & DODRT_HOST_BUILD_KEEP_CREATION_ORDER)) {
+        // Triangle::reorderLanesByIndices, triangle.cpp:349-367
+        std::vector<TriLane> lanes;
+        std::vector<NormalLane> normals;
+        std::vector<AttrLane> attrs;
+        gatherLanes(s->lanes, s->primNums, lanes, threads);
+        s->lanes.swap(lanes);
+        std::vector<TriLane>().swap(lanes);
+        gatherLanes(s->normals, s->primNums, normals, threads);
+        s->normals.swap(normals);
+        std::vector<NormalLane>().swap(normals);
+        gatherLanes(s->attrs, s->primNums, attrs, threads);
+        s->attrs.swap(attrs);
     }
-    s->lanes.swap(lanes);
-    s->normals.swap(normals);
-    s->attrs.swap(attrs);
+    s->creationOrder = (flags & DODRT_HOST_BUILD_KEEP_CREATION_ORDER) != 0;
+    s->buildSeconds = std::chrono::duration<double>(t1 - t0).count();
+    s->reorderSeconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - t1).count();
+    if (std::getenv("DODRT_HOST_VERBOSE")) {
+        std::fprintf(stderr, "dodrt_host: kd build %.3f s, lane re-order %.3f s, %u threads, %zu nodes, %zu lanes\n",
+                     s->buildSeconds, s->reorderSeconds, threads, s->nodes.size(), s->primNums.size());
+    }
     for (int i = 0; i < 3; i++) {
         s->boundsOut[i] = s->bounds.lo[i];
         s->boundsOut[3 + i] = s->bounds.hi[i];
@@ -748,13 +890,15 @@ int dodrt_host_build_tree(dodrt_host_scene *s)
     return DODRT_OK;
 }
 
+int dodrt_host_build_tree(dodrt_host_scene *s) { return dodrt_host_build_tree_ex(s, 0); }
+
 int dodrt_host_sizes_get(const dodrt_host_scene *s, dodrt_host_sizes *z)
 {
     if (!s || !z) return fail("NULL argument");
     z->num_triangles = s->numTriangles;
     z->num_orig_lanes = s->built ? s->numOrigLanes : (uint32_t)s->lanes.size();
     z->num_nodes = (uint32_t)s->nodes.size();
-    z->num_lanes = (uint32_t)s->lanes.size();
+    z->num_lanes = s->built ? (uint32_t)s->primNums.size() : (uint32_t)s->lanes.size();
     z->max_depth = s->maxDepth;
     z->num_spheres = s->numSpheres;
     z->num_planes = s->numPlanes;

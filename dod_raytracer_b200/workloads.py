@@ -146,7 +146,7 @@ def _dragon_instances(w: Workload):
     return inst
 
 
-def build_host_scene(w: Workload, mesh_files=None) -> host.HostScene:
+def build_host_scene(w: Workload, mesh_files=None, keep_creation_order: bool = False) -> host.HostScene:
     """Scene registration in the reference's order: spheres, planes, cylinder, meshes, buildTree (main.cpp:364-368).
     Meshes are added from `mesh_files` when given (so that the CPU baseline and the GPU path read the very same
     bytes), otherwise generated in memory with the same arithmetic."""
@@ -170,5 +170,6 @@ def build_host_scene(w: Workload, mesh_files=None) -> host.HostScene:
                 p = (pos * np.float32(scale) + np.asarray(tr, np.float32)).astype(np.float32)
                 hs.add_mesh(p, idx)
     if w.mesh != "none":
-        hs.build_tree()
+        # keep_creation_order: skip the host-side lane re-order, upload() lets the GPU do it (f-4)
+        hs.build_tree(keep_creation_order=keep_creation_order)
     return hs

@@ -87,12 +87,21 @@ DODRT_API int dodrt_host_add_reference_scene(dodrt_host_scene *scene, uint32_t s
 DODRT_API int dodrt_host_add_analytic_scene(dodrt_host_scene *scene, uint32_t seed, uint32_t count);
 
 /* ---- kd-tree ------------------------------------------------------------------------------------------ */
+/* KDTree::buildTree() (kdtree.cpp:252-260): SAH build + Triangle::reorderLanesByIndices.  The build is
+ * task-parallel over subtrees (env DODRT_HOST_THREADS, default = all cores) and returns the reference's tree bit for
+ * bit for every thread count (see TreeBuilder in dodrt_host.cpp). */
 DODRT_API int dodrt_host_build_tree(dodrt_host_scene *scene);
+/* flags: DODRT_HOST_BUILD_KEEP_CREATION_ORDER skips the host-side lane re-order (triangle.cpp:349-367, a gather that
+ * multiplies the lane data by the tree's duplication factor): dodrt_host_tri_lanes / _tri_normals / _tri_attributes
+ * then stay in CREATION order (num_orig_lanes records) and the re-order runs on the GPU at upload
+ * (dodrt_scene_set_kdtree_indexed / dodrt_scene_set_shading_indexed with dodrt_host_prim_nums). */
+#define DODRT_HOST_BUILD_KEEP_CREATION_ORDER 1u
+DODRT_API int dodrt_host_build_tree_ex(dodrt_host_scene *scene, uint32_t flags);
 
 /* ---- export: pointers stay valid until the scene is modified or destroyed ---------------------------- */
 DODRT_API int dodrt_host_sizes_get(const dodrt_host_scene *scene, dodrt_host_sizes *sizes);
 DODRT_API const uint64_t *dodrt_host_nodes(const dodrt_host_scene *scene);
-DODRT_API const float *dodrt_host_tri_lanes(const dodrt_host_scene *scene);    /* re-ordered, 72 floats each */
+DODRT_API const float *dodrt_host_tri_lanes(const dodrt_host_scene *scene);    /* re-ordered (see build flags), 72 floats each */
 DODRT_API const uint32_t *dodrt_host_prim_nums(const dodrt_host_scene *scene); /* original lane of each lane */
 DODRT_API const float *dodrt_host_bounds(const dodrt_host_scene *scene);       /* 6 floats */
 DODRT_API const float *dodrt_host_tri_normals(const dodrt_host_scene *scene);  /* re-ordered, 9 floats / slot */

@@ -21,7 +21,7 @@ def sha(a):
     return hashlib.sha256(np.ascontiguousarray(a).tobytes()).hexdigest()
 
 
-@pytest.fixture(scope="module", params=[0, 1, 2, 3, 4, 5], ids=lambda v: f"variant{v}")
+@pytest.fixture(scope="module", params=[0, 1, 2, 3, 4, 5, 6], ids=lambda v: f"variant{v}")
 def teapot(request):
     """every kernel variant must return the same bits"""
     scene = teapot_scene(full=True)
@@ -243,7 +243,7 @@ def test_full_reference_frame_pixels_within_one_255th():
     want = np.load(f"{GOLDEN}/teapot_render_240x135.npz")["rgb"].astype(np.int32)
     h, w = want.shape[:2]
     xs, ys = host.ray_tables(w, h)
-    for variant in (3, 0, 4):
+    for variant in (3, 0, 4, 6):
         with _render_scene().upload(0, shading=True) as g:
             g.set_kernel_variant(variant)
             got = g.render(capi.Frame.make(w, h, classes=ALL), xs, ys, workloads.REFERENCE_LIGHTS,
@@ -271,3 +271,33 @@ def test_render_against_live_reference_other_sizes_and_depths():
         # depth 1 (primary + 9 shadow passes) is still a sane image and differs from depth 10
         d1 = g.render(capi.Frame.make(160, 90, classes=ALL), *host.ray_tables(160, 90), workloads.REFERENCE_LIGHTS, 1)
         assert d1.mean() > 10 and np.abs(d1.astype(np.int32) - ref.render(160, 90, nthreads=1)).max() > 1
+
+
+def test_gpu_side_lane_reorder_matches_host_reorder():
+    """f-4: dodrt_scene_set_kdtree_indexed / _set_shading_indexed (Triangle::reorderLanesByIndices, triangle.cpp:349-367,
+    done by the upload kernels from the lanes in creation order + m_primNums) give the same scene as the host-side
+    re-order: identical hit records, visibility bytes and rendered pixels."""
+    from dod_raytracer_b200 import host, workloads
+
+    def scene(keep):
+        hs = host.HostScene()
+        hs.add_reference_scene(1, 16)
+        hs.add_mesh_file(f"{GOLDEN}/teapot.dodm")
+        hs.build_tree(keep_creation_order=keep)
+        return hs
+
+    w, h = 480, 270
+    xs, ys = host.ray_tables(w, h)
+    out = []
+    for keep in (False, True):
+        hs = scene(keep)
+        assert hs.sizes().num_lanes == 3021 and hs.sizes().num_orig_lanes == 790  # SURVEY.md 4: teapot pins
+        with hs.upload(0, shading=True) as g:
+            frame = capi.Frame.make(w, h, classes=ALL)
+            hits, vis = g.trace_frame(frame, xs, ys, LIGHT0[None, :])
+            rgb = g.render(frame, xs, ys, workloads.REFERENCE_LIGHTS, 3)
+            out.append((hits.tobytes(), vis.tobytes(), rgb.tobytes()))
+    assert out[0][0] == out[1][0], "hit records differ"
+    assert out[0][1] == out[1][1], "visibility differs"
+    assert out[0][2] == out[1][2], "rendered pixels differ"
+    assert (np.frombuffer(out[0][0], capi.HIT_DT)["prim"] >> 29 == 0).sum() > 1000  # the teapot is in view
