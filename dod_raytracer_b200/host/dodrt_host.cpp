@@ -312,10 +312,22 @@ bool readFile(const char *path, std::vector<char> &buf)
     return true;
 }
 
-void parseObj(const std::vector<char> &buf, std::vector<Vec3> &pos, std::vector<uint32_t> &idx)
+unsigned hostThreads();
+
+// One chunk of an OBJ text (whole lines).  Positive `f` indices are absolute; negative ones count back from the number
+// of `v` lines seen so far IN THE FILE, which a chunk does not know -- they are stored as (negative value, number of
+// v lines seen so far in this chunk) and resolved once the chunks' vertex counts are known.
+struct ObjChunk {
+    std::vector<Vec3> pos;
+    static constexpr uint32_t kAbsolute = 0xFFFFFFFFu;
+    std::vector<long> corners;       // 3 per triangle: absolute vertex index, or (<= 0) relative, see `localSeen`
+    std::vector<uint32_t> localSeen; // per corner: kAbsolute, or the v lines of this chunk before the face
+};
+
+void parseObjChunk(const char *p, const char *end, ObjChunk &out)
 {
-    const char *p = buf.data(), *end = p + buf.size();
     std::vector<long> corners;
+    std::vector<uint32_t> seen;
     std::string line;
     while (p < end) {
         const char *eol = static_cast<const char *>(std::memchr(p, '\n', (size_t)(end - p)));
@@ -330,7 +342,7 @@ void parseObj(const std::vector<char> &buf, std::vector<Vec3> &pos, std::vector<
             v.x = strtof(c + 2, &q);
             v.y = strtof(q, &q);
             v.z = strtof(q, &q);
-            pos.push_back(v);
+            out.pos.push_back(v);
         } else if (c[0] == 'f' && (c[1] == ' ' || c[1] == '\t')) {
             corners.clear();
             c += 2;
@@ -340,16 +352,49 @@ void parseObj(const std::vector<char> &buf, std::vector<Vec3> &pos, std::vector<
                 char *q = nullptr;
                 long v = strtol(c, &q, 10);
                 if (q == c) break;
-                corners.push_back(v > 0 ? v - 1 : (long)pos.size() + v);
+                corners.push_back(v);
                 c = q;
                 while (*c && *c != ' ' && *c != '\t' && *c != '\r') c++; // skip /vt/vn
             }
             for (size_t k = 1; k + 1 < corners.size(); k++) { // fan triangulation
-                idx.push_back((uint32_t)corners[0]);
-                idx.push_back((uint32_t)corners[k]);
-                idx.push_back((uint32_t)corners[k + 1]);
+                const long tri[3] = {corners[0], corners[k], corners[k + 1]};
+                for (long v : tri) { // v > 0: 1-based absolute; v <= 0: relative to the vertices seen so far
+                    out.corners.push_back(v > 0 ? v - 1 : v);
+                    out.localSeen.push_back(v > 0 ? ObjChunk::kAbsolute : (uint32_t)out.pos.size());
+                }
             }
         }
+    }
+}
+
+// `v x y z` (strtof, the loader law of DESIGN.md) and `f a b c ...` lines; everything else is ignored.  The text is
+// cut at line ends into one chunk per host thread, parsed concurrently and concatenated in file order -- the same
+// values as a sequential pass.
+void parseObj(const std::vector<char> &buf, std::vector<Vec3> &pos, std::vector<uint32_t> &idx)
+{
+    const char *base = buf.data(), *end = base + buf.size();
+    size_t numChunks = std::max<size_t>(1, std::min<size_t>(hostThreads(), buf.size() / (1u << 20)));
+    std::vector<const char *> cut(numChunks + 1, end);
+    cut[0] = base;
+    for (size_t k = 1; k < numChunks; k++) {
+        const char *p = base + buf.size() * k / numChunks;
+        if (p < cut[k - 1]) p = cut[k - 1];
+        const char *eol = static_cast<const char *>(std::memchr(p, '\n', (size_t)(end - p)));
+        cut[k] = eol ? eol + 1 : end;
+    }
+    std::vector<ObjChunk> chunks(numChunks);
+    std::vector<std::thread> pool;
+    for (size_t k = 1; k < numChunks; k++) pool.emplace_back([&, k] { parseObjChunk(cut[k], cut[k + 1], chunks[k]); });
+    parseObjChunk(cut[0], cut[1], chunks[0]);
+    for (std::thread &t : pool) t.join();
+    size_t seenBefore = 0;
+    for (const ObjChunk &c : chunks) {
+        for (size_t i = 0; i < c.corners.size(); i++) {
+            const long v = c.corners[i];
+            idx.push_back((uint32_t)(c.localSeen[i] == ObjChunk::kAbsolute ? v : (long)(seenBefore + c.localSeen[i]) + v));
+        }
+        pos.insert(pos.end(), c.pos.begin(), c.pos.end());
+        seenBefore += c.pos.size();
     }
 }
 

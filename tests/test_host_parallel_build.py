@@ -64,3 +64,52 @@ def test_sizes_in_creation_order_mode():
     assert hs.arrays()["tri_lanes"].shape[0] == z.num_lanes  # default view: gathered through prim_nums
     with pytest.raises(RuntimeError):
         hs.build_tree()
+
+
+_OBJ_CHILD = r"""
+import hashlib, sys
+import numpy as np
+sys.path.insert(0, {root!r})
+from dod_raytracer_b200 import host
+hs = host.HostScene()
+hs.add_mesh_file({path!r})
+a = hs.arrays(normals=True)
+print(hs.sizes().num_triangles, hashlib.sha256(a["tri_lanes"].tobytes() + a["tri_normals"].tobytes()).hexdigest())
+"""
+
+
+def test_chunked_obj_parse_equals_sequential(tmp_path):
+    """the OBJ text is parsed in per-thread chunks cut at line ends; negative (relative) indices and polygons must
+    resolve exactly as in one sequential pass"""
+    pos, idx = host.standin_dragon(180)
+    path = tmp_path / "big.obj"
+    rng = np.random.default_rng(7)
+    with open(path, "w") as f:
+        # vertices and faces interleaved in blocks, so relative indices cross chunk borders
+        done_v = 0
+        order = np.argsort(idx.max(axis=1), kind="stable")
+        faces = idx[order]
+        need = faces.max(axis=1)
+        k = 0
+        for block in range(0, len(pos), 997):
+            hi = min(len(pos), block + 997)
+            for p in pos[block:hi]:
+                f.write(f"v {p[0]:.9g} {p[1]:.9g} {p[2]:.9g}\n")
+            done_v = hi
+            while k < len(faces) and need[k] < done_v:
+                a, b, c = (int(x) for x in faces[k])
+                if rng.random() < 0.5:  # relative form: -1 = last vertex seen
+                    f.write(f"f {a - done_v} {b - done_v}/1/1 {c - done_v}//3\n")
+                else:
+                    f.write(f"f {a + 1} {b + 1} {c + 1}\n")
+                k += 1
+            f.write("# comment\nvn 0 0 1\n")
+        assert k == len(faces)
+    assert os.path.getsize(path) > 2 << 20  # at least two 1-MiB chunks
+    out = []
+    for threads in (1, 8):
+        env = dict(os.environ, DODRT_HOST_THREADS=str(threads))
+        code = _OBJ_CHILD.format(root=ROOT, path=str(path))
+        out.append(subprocess.run([sys.executable, "-c", code], check=True, capture_output=True, text=True, env=env).stdout)
+    assert out[0] == out[1]
+    assert int(out[0].split()[0]) == len(idx)
