@@ -252,7 +252,11 @@ int launchFrame(dodrt_scene *s, TraceMode mode, const dodrt_frame *frame, const 
         if (rc != DODRT_OK) return rc;
         CUDA_TRY(cudaMallocFromPoolAsync(&p.tile_order, sizeof(uint32_t) * tiles, s->pool, stream));
     }
-    cudaError_t le = launch_trace(mode, p, s->cfg[p.variant][mode], stream);
+    if (p.variant == kDonateVariant) {
+        int rc = ensurePool(s);
+        if (rc != DODRT_OK) return rc;
+    }
+    cudaError_t le = launch_trace(mode, p, s->cfg[p.variant][mode], stream, s->pool);
     if (p.tile_order) {
         cudaFreeAsync(p.tile_order, stream);
         s->launches.fetch_add(1);
@@ -296,7 +300,10 @@ int dodrt_scene_create(int device, dodrt_scene **scene)
         const char *t = std::getenv("DODRT_TUNE"); // "num,den,maxNodeRun" (exploration knob)
         unsigned a = 3, b = 1, c = 0xFFFFFFFFu; // measured best on dragon4k (profiles/r01_vote_rule_sweep.txt)
         if (t) std::sscanf(t, "%u,%u,%u", &a, &b, &c);
-        s->dev.tune[0] = a, s->dev.tune[1] = b, s->dev.tune[2] = c, s->dev.tune[3] = 0;
+        s->dev.tune[0] = a, s->dev.tune[1] = b, s->dev.tune[2] = c;
+        // test knob for variant 7: suspend rays at every poll, helpers or not (exercises the resume path everywhere)
+        const char *always = std::getenv("DODRT_DONATE_ALWAYS");
+        s->dev.tune[3] = (always && std::atoi(always) != 0) ? 1u : 0u;
     }
     cudaError_t e = cudaMalloc(&s->d_counters, sizeof(unsigned long long) * kCounterSlots * kCounterWords);
     s->variant = default_variant();
@@ -656,7 +663,11 @@ int dodrt_intersect_device(dodrt_scene *s, const dodrt_ray *d_rays, uint64_t num
     p.variant = s->variant;
     p.tile_order = nullptr;
     p.num_local_tiles = 0;
-    CUDA_TRY(launch_trace(kModeRays, p, s->cfg[p.variant][kModeRays], static_cast<cudaStream_t>(stream)));
+    if (p.variant == kDonateVariant) {
+        int rc = ensurePool(s);
+        if (rc != DODRT_OK) return rc;
+    }
+    CUDA_TRY(launch_trace(kModeRays, p, s->cfg[p.variant][kModeRays], static_cast<cudaStream_t>(stream), s->pool));
     s->launches.fetch_add(1);
     return DODRT_OK;
 }
@@ -947,13 +958,13 @@ int dodrt_render(dodrt_scene *s, const dodrt_frame *frame, const float *xs, cons
         p.hits = rp.hits;
         p.variant = s->variant;
         p.counter = nextCounter(s);
-        e = launch_trace(kModeRays, p, s->cfg[p.variant][kModeRays], st); // closest-hit chain, main.cpp:314-321
+        e = launch_trace(kModeRays, p, s->cfg[p.variant][kModeRays], st, s->pool); // closest-hit chain, main.cpp:314-321
         if (e == cudaSuccess) s->launches.fetch_add(1);
         for (uint32_t l = 0; l < num_lights && e == cudaSuccess; l++) { // canSeeLight per light, main.cpp:226
             p.counter = nextCounter(s);
             p.visible = rp.visible + n * l;
             for (int c = 0; c < 3; c++) p.light[c] = rp.lights[l][c];
-            e = launch_trace(kModeShadowRays, p, s->cfg[p.variant][kModeShadowRays], st);
+            e = launch_trace(kModeShadowRays, p, s->cfg[p.variant][kModeShadowRays], st, s->pool);
             if (e == cudaSuccess) s->launches.fetch_add(1);
         }
         if (e == cudaSuccess) e = launch_render_shade(rp, k, st);

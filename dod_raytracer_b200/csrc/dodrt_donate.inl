@@ -1,0 +1,274 @@
+// dodrt_donate.inl -- variant 7: variant 3 plus RAY DONATION at the tail of a pass.
+// Textually included by dodrt_kernels.cu inside namespace dodrt::{anonymous}.
+//
+// Why (profiles/r01_rank_tail.txt): a persistent pass ends with its slowest warp, and a 32-ray batch grazing the
+// mesh runs 0.2-0.5 ms on a lone warp -- as long as a whole 8-GPU share of the frame.  The SMs that have run out of
+// work idle meanwhile (rank 0 of 8: 44 % busy in the primary pass).
+//
+// How: a warp that cannot claim another batch does not exit; it becomes a HELPER and waits on a global queue.
+// A warp still traversing polls (one volatile load every kDonatePoll voted iterations) whether helpers exist; if
+// they outnumber the queued rays it SUSPENDS its live rays -- ray, running clip, best hit, node / leaf cursor and
+// the short stack -- into the queue and goes on to become a helper itself.  A helper resumes ONE ray with the whole
+// warp: kd node steps are warp-uniform, a leaf is tested 32 triangle slots at a time and reduced with the
+// lexicographic (t, slot) minimum, which is what the reference's slot-by-slot loop with its strict `<` leaves behind
+// (triangle.cpp:119-139) -- the same reduction as leaf_step_coop, bit-identical to every other variant.
+// A suspended ray resumes exactly where it stopped: no node is visited twice, the order of events per ray is the
+// reference's (kdtree.cpp:263-361).  All blocks of the launch are co-resident (grid = one wave), so waiting on the
+// queue cannot deadlock; the pass ends when every warp has left the main loop and the queue is empty.
+constexpr uint32_t kDonatePoll = 32;
+enum FinishKind : uint32_t { kFinishRecord = 0, kFinishAnyRecord = 1, kFinishVisible = 2 };
+
+// What remains to be done with the kd-tree's answer for one ray (main.cpp:320-325 / 209-217 as the trace kernel
+// applies them): where the result goes and what it is when the tree finds nothing.
+struct Finish {
+    uint64_t out;
+    uint32_t kind;
+    float pre[4]; // kFinishRecord: the record before the tree (analytic hit or miss); kFinishAnyRecord: pre[0] = the ray's clip
+};
+
+__device__ __forceinline__ void finish_write(const TraceParams &p, uint32_t kind, uint64_t out, bool found, const Hit &hit,
+                                             const float pre[4])
+{
+    if (kind == kFinishVisible) {
+        p.visible[out] = found ? 0 : 1;
+    } else if (kind == kFinishAnyRecord) {
+        reinterpret_cast<float4 *>(p.hits)[out] = make_float4(pre[0], __uint_as_float(found ? 0u : DODRT_MISS), 0.0f, 0.0f);
+    } else if (found) {
+        reinterpret_cast<float4 *>(p.hits)[out] = make_float4(hit.t, __uint_as_float(hit.prim), hit.u, hit.v);
+    } else {
+        reinterpret_cast<float4 *>(p.hits)[out] = make_float4(pre[0], pre[1], pre[2], pre[3]);
+    }
+}
+
+__device__ __forceinline__ unsigned long long ld_volatile_u64(const unsigned long long *p)
+{
+    return *reinterpret_cast<const volatile unsigned long long *>(p);
+}
+
+// Queue protocol (counters kDonateFinished / kDonateHead / kDonateTail, on their own 128-B line):
+//   * a helper takes a TICKET h = atomicAdd(head, 1) and then waits on ready[h] alone -- a word nobody else polls;
+//   * donors reserve slots with atomicAdd(tail, n), fill them, fence, and set ready[slot];
+//   * head - tail (when positive) is the number of helpers waiting with a ticket and no ray: donors give at most
+//     that many rays, so a ray is only ever suspended when a whole warp is idle and waiting for it;
+//   * a ticket holder whose slot was never filled leaves when every warp has left its main loop (no donor is left)
+//     and tail <= its ticket.
+// Donor side, called by every lane of the warp: should this warp suspend rays now, and how many at most?
+__device__ __noinline__ uint32_t donate_poll_impl(const unsigned long long *counter, uint32_t capacity, uint32_t always)
+{
+    uint32_t want = 0;
+    if ((threadIdx.x & 31u) == 0u) {
+        const unsigned long long head = ld_volatile_u64(counter + kDonateHead);
+        const unsigned long long tail = ld_volatile_u64(counter + kDonateTail);
+        if (tail <= capacity / 2u) {
+            if (always != 0u) {
+                want = 32u;
+            } else if (head > tail) {
+                want = (uint32_t)(head - tail < 32ull ? head - tail : 32ull);
+            }
+        }
+    }
+    return __shfl_sync(0xffffffffu, want, 0);
+}
+__device__ __forceinline__ uint32_t donate_poll(const TraceParams &p) { return donate_poll_impl(p.counter, p.donate_capacity, p.scene.tune[3]); }
+
+// Everything a helper needs to resume one ray.  The suspension is a cold path: the donor packs this struct (a few
+// dozen stores to local memory, executed only when a ray is actually given away) and a NON-INLINED routine copies it
+// into the queue, so the register allocation of the hot voted loop does not have to keep all of it live together with
+// the temporaries of the copy (inlined, the suspension raised the kernels from 96 to 114 registers = 5 -> 4 blocks
+// per SM).
+struct SuspendedRay {
+    float4 w[6]; // w[3] and the `out` half of w[5] are filled by donate_store from the Finish record
+    const uint32_t *stackNode;
+    const float *stackTmin, *stackTmax;
+    int sp;
+};
+
+// `fin` lives in the caller's local memory (its address escapes to this non-inlined routine), so the finisher
+// record -- never read by the traversal itself -- does not occupy registers across the voted loop.
+__device__ __noinline__ void donate_store(uint32_t *slots, uint32_t *ready, uint32_t slot, const SuspendedRay &r,
+                                          const Finish *fin)
+{
+    float4 *w = reinterpret_cast<float4 *>(slots + (size_t)slot * kDonateSlotWords);
+    w[0] = r.w[0];
+    w[1] = make_float4(r.w[1].x, r.w[1].y, r.w[1].z, __uint_as_float(__float_as_uint(r.w[1].w) | (fin->kind << 2)));
+    w[2] = r.w[2];
+    w[3] = make_float4(fin->pre[0], fin->pre[1], fin->pre[2], fin->pre[3]);
+    w[4] = r.w[4];
+    w[5] = make_float4(r.w[5].x, r.w[5].y, __uint_as_float((uint32_t)fin->out), __uint_as_float((uint32_t)(fin->out >> 32)));
+    uint32_t *stk = slots + (size_t)slot * kDonateSlotWords + 24;
+    for (int i = 0; i < r.sp; i++) {
+        stk[3 * i + 0] = r.stackNode[i];
+        stk[3 * i + 1] = __float_as_uint(r.stackTmin[i]);
+        stk[3 * i + 2] = __float_as_uint(r.stackTmax[i]);
+    }
+    __threadfence();
+    *reinterpret_cast<volatile uint32_t *>(ready + slot) = 1u;
+}
+
+// Suspends up to `want` live rays of the warp into the queue (lanes in ascending order).  The lanes concerned have
+// st.live == false and donated == true afterwards.
+__device__ __forceinline__ void donate_live_rays(const TraceParams &p, uint32_t want, TreeState &st, const float o[3],
+                                                 const float d[3], bool any, float clip, const Hit &hit, bool found,
+                                                 const Finish *fin, const uint32_t *stackNode, const float *stackTmin,
+                                                 const float *stackTmax, bool &donated)
+{
+#ifdef DBG_NODONATE
+    return;
+#endif
+    const uint32_t lane = threadIdx.x & 31u;
+    const unsigned candidates = __ballot_sync(0xffffffffu, st.live && st.sp <= kDonateMaxStack);
+    const uint32_t rank = __popc(candidates & ((1u << lane) - 1u));
+    const bool give = ((candidates >> lane) & 1u) != 0u && rank < want;
+    const uint32_t n = min((uint32_t)__popc(candidates), want);
+    if (n == 0u) {
+        return;
+    }
+    unsigned long long base = 0;
+    if (lane == 0) {
+        base = atomicAdd(p.counter + kDonateTail, (unsigned long long)n);
+    }
+    base = __shfl_sync(0xffffffffu, base, 0);
+    if (give) {
+        SuspendedRay r;
+        const uint32_t flags = (any ? 1u : 0u) | (found ? 2u : 0u);
+        r.w[0] = make_float4(o[0], o[1], o[2], d[0]);
+        r.w[1] = make_float4(d[1], d[2], clip, __uint_as_float(flags));
+        r.w[2] = make_float4(hit.t, __uint_as_float(hit.prim), hit.u, hit.v);
+        r.w[4] = make_float4(st.tmin, st.tmax, __uint_as_float(st.node), __uint_as_float(st.triCur));
+        r.w[5] = make_float4(__uint_as_float(st.triEnd), __uint_as_float((uint32_t)st.sp), 0.0f, 0.0f);
+        r.stackNode = stackNode;
+        r.stackTmin = stackTmin;
+        r.stackTmax = stackTmax;
+        r.sp = st.sp;
+        donate_store(p.donate_slots, p.donate_ready, (uint32_t)base + rank, r, fin);
+        st.live = false;
+        donated = true;
+    }
+}
+
+// Helper side: the whole warp resumes the ray in `slot` and writes its result.
+__device__ __forceinline__ void resume_ray(const TraceParams &p, uint32_t slot)
+{
+    const DeviceScene &s = p.scene;
+    const uint32_t lane = threadIdx.x & 31u;
+    const float4 *w = reinterpret_cast<const float4 *>(p.donate_slots + (size_t)slot * kDonateSlotWords);
+    const float4 w0 = __ldcg(w), w1 = __ldcg(w + 1), w2 = __ldcg(w + 2), w3 = __ldcg(w + 3), w4 = __ldcg(w + 4),
+                 w5 = __ldcg(w + 5);
+    const float o[3] = {w0.x, w0.y, w0.z}, d[3] = {w0.w, w1.x, w1.y};
+    float clip = w1.z;
+    const uint32_t flags = __float_as_uint(w1.w);
+    const bool any = (flags & 1u) != 0u;
+    bool found = (flags & 2u) != 0u;
+    const uint32_t kind = flags >> 2;
+    Hit hit;
+    hit.t = w2.x, hit.prim = __float_as_uint(w2.y), hit.u = w2.z, hit.v = w2.w;
+    const float pre[4] = {w3.x, w3.y, w3.z, w3.w};
+    TreeState st;
+    st.inv[0] = 1.0f / d[0]; // kdtree.cpp:271, the same division the donor did
+    st.inv[1] = 1.0f / d[1];
+    st.inv[2] = 1.0f / d[2];
+    st.tmin = w4.x, st.tmax = w4.y, st.node = __float_as_uint(w4.z), st.triCur = __float_as_uint(w4.w);
+    st.triEnd = __float_as_uint(w5.x);
+    st.sp = (int)__float_as_uint(w5.y);
+    st.live = true;
+    const uint64_t out = (uint64_t)__float_as_uint(w5.z) | ((uint64_t)__float_as_uint(w5.w) << 32);
+    uint32_t stackNode[kMaxStack];
+    float stackTmin[kMaxStack];
+    float stackTmax[kMaxStack];
+    const uint32_t *stk = p.donate_slots + (size_t)slot * kDonateSlotWords + 24;
+    for (int i = 0; i < st.sp; i++) {
+        stackNode[i] = __ldcg(stk + 3 * i);
+        stackTmin[i] = __uint_as_float(__ldcg(stk + 3 * i + 1));
+        stackTmax[i] = __uint_as_float(__ldcg(stk + 3 * i + 2));
+    }
+    while (st.live) { // warp-uniform: every lane holds the same state
+        if (st.triCur < st.triEnd) {
+            const uint32_t tri = st.triCur + lane;
+            bool acc = false;
+            float t = 0.0f, u = 0.0f, v = 0.0f;
+            if (tri < st.triEnd) {
+                const float *base = reinterpret_cast<const float *>(s.lanes4) + (size_t)(tri >> 3) * 72 + (tri & 7u);
+                const float4 q0 = make_float4(__ldg(base), __ldg(base + 8), __ldg(base + 16), __ldg(base + 24));
+                const float4 q1 = make_float4(__ldg(base + 32), __ldg(base + 40), __ldg(base + 48), __ldg(base + 56));
+                const float4 q2 = make_float4(__ldg(base + 64), 0.0f, 0.0f, 0.0f);
+                acc = triangle_test_fast(q0, q1, q2, o, d, clip, t, u, v);
+            }
+            const unsigned accMask = __ballot_sync(0xffffffffu, acc);
+            if (accMask != 0u) {
+                float best = acc ? t : kInfinity; // accepted t are finite and positive: min() is exact
+#pragma unroll
+                for (uint32_t off = 16; off != 0u; off >>= 1) {
+                    best = fminf(best, __shfl_xor_sync(0xffffffffu, best, off));
+                }
+                const unsigned winners = __ballot_sync(0xffffffffu, acc && t == best);
+                const uint32_t src = (uint32_t)__ffs((int)winners) - 1u; // lowest slot id among equal t
+                clip = best;
+                hit.t = best;
+                hit.prim = (DODRT_KIND_TRIANGLE << DODRT_KIND_SHIFT) | (st.triCur + src);
+                hit.u = __shfl_sync(0xffffffffu, u, src);
+                hit.v = __shfl_sync(0xffffffffu, v, src);
+                found = true;
+            }
+            st.triCur = st.triCur + 32u < st.triEnd ? st.triCur + 32u : st.triEnd;
+            if (any && found) {
+                st.live = false; // kdtree.cpp:338-341
+            } else if (st.triCur == st.triEnd) {
+                tree_pop(st, stackNode, stackTmin, stackTmax);
+            }
+        } else {
+            node_step(s, st, o, d, clip, stackNode, stackTmin, stackTmax);
+        }
+    }
+    if (lane == 0) {
+        finish_write(p, kind, out, found, hit, pre);
+    }
+}
+
+// Runs after the main loop of a warp: count this warp as finished, then serve the queue -- take a ticket, wait for that
+// slot to be filled, resume the ray -- until every warp has left its main loop and no slot at or beyond the ticket
+// was reserved.
+__device__ __forceinline__ void donate_helper_loop(const TraceParams &p)
+{
+    const uint32_t lane = threadIdx.x & 31u;
+    const unsigned long long totalWarps = (unsigned long long)gridDim.x * (blockDim.x >> 5);
+    if (lane == 0) {
+        __threadfence(); // this warp's donations (if any) are published before it counts as finished
+        atomicAdd(p.counter + kDonateFinished, 1ull);
+    }
+    for (;;) {
+        uint32_t ticket = 0;
+        if (lane == 0) {
+            ticket = (uint32_t)atomicAdd(p.counter + kDonateHead, 1ull);
+        }
+        ticket = __shfl_sync(0xffffffffu, ticket, 0);
+        if (ticket >= p.donate_capacity) {
+            break; // cannot happen while donors respect the capacity bound; never index past the queue
+        }
+        uint32_t ready = 0;
+        if (lane == 0) {
+            unsigned ns = 200;
+            for (;;) {
+                if (*reinterpret_cast<const volatile uint32_t *>(p.donate_ready + ticket) != 0u) {
+                    ready = 1;
+                    break;
+                }
+                if (ld_volatile_u64(p.counter + kDonateFinished) == totalWarps) {
+                    // no donor is left: slots below tail are filled or being filled by warps that counted as finished
+                    // only after publishing them, so tail is final here
+                    __threadfence();
+                    if (ld_volatile_u64(p.counter + kDonateTail) <= ticket) {
+                        break;
+                    }
+                }
+                __nanosleep(ns);
+                ns = ns < 3200u ? ns * 2u : ns;
+            }
+        }
+        ready = __shfl_sync(0xffffffffu, ready, 0);
+        if (!ready) {
+            break;
+        }
+        __threadfence();
+        resume_ray(p, ticket);
+    }
+}

@@ -24,6 +24,8 @@
 //   5  variant 3 plus a cooperative leaf step for stragglers (<= 4 rays waiting: 8/16/32 lanes per ray).
 //   6  variant 3 with the branch-free first stage on packed fp32 pairs (FMUL2/FADD2/FFMA2, dodrt_device.cuh): half
 //      the fp32 issue slots for the same bits.
+//   7  variant 3 plus ray donation at the tail of a pass (dodrt_donate.inl): warps that ran out of work resume,
+//      32 lanes wide, the rays suspended by warps that are still traversing.
 // Every variant computes identical results (parity tests run all of them).
 #include "dodrt_kernels.cuh"
 #include "dodrt_prim_bvh.cuh"
@@ -323,9 +325,12 @@ __device__ __forceinline__ void leaf_step_coop(const DeviceScene &s, TreeState &
     }
 }
 
-template <bool SOA, bool SHARE, bool PACKED>
+#include "dodrt_donate.inl"
+
+template <bool SOA, bool SHARE, bool PACKED, bool DONATE>
 __device__ __forceinline__ bool kdtree_query_voted(const DeviceScene &s, bool enter, const float o[3], const float d[3],
-                                                   bool any, float &clip, Hit &hit)
+                                                   bool any, float &clip, Hit &hit, const TraceParams *p = nullptr,
+                                                   const Finish *fin = nullptr, bool *donated = nullptr)
 {
     TreeState st;
     tree_enter(s, st, enter, o, d, clip);
@@ -334,28 +339,47 @@ __device__ __forceinline__ bool kdtree_query_voted(const DeviceScene &s, bool en
     float stackTmax[kMaxStack];
     bool found = false;
     uint32_t nodeRun = 0;
+    // The voted loop proper contains no atomics, volatile loads or calls; with DONATE it is left every kDonatePoll
+    // iterations for the poll / suspension below and re-entered (ptxas puts a YIELD at the head of a loop that
+    // contains the poll, which cost the shadow pass 17 %).
     for (;;) {
-        const bool wantLeaf = st.live && st.triCur < st.triEnd;
-        const bool wantNode = st.live && !wantLeaf;
-        const unsigned leafMask = __ballot_sync(0xffffffffu, wantLeaf);
-        const unsigned nodeMask = __ballot_sync(0xffffffffu, wantNode);
-        if ((leafMask | nodeMask) == 0u) {
+        bool finished = false;
+        uint32_t budget = kDonatePoll;
+        for (;;) {
+            const bool wantLeaf = st.live && st.triCur < st.triEnd;
+            const bool wantNode = st.live && !wantLeaf;
+            const unsigned leafMask = __ballot_sync(0xffffffffu, wantLeaf);
+            const unsigned nodeMask = __ballot_sync(0xffffffffu, wantNode);
+            if ((leafMask | nodeMask) == 0u) {
+                finished = true;
+                break;
+            }
+            const uint32_t nLeaf = __popc(leafMask), nNode = __popc(nodeMask);
+            if (nNode == 0u || (nLeaf != 0u && (nLeaf * s.tune[1] >= nNode * s.tune[0] || nodeRun >= s.tune[2]))) {
+                nodeRun = 0;
+                if (SHARE && nLeaf <= 4u) {
+                    leaf_step_coop(s, st, leafMask, nLeaf, wantLeaf, o, d, any, clip, hit, found, stackNode, stackTmin,
+                                   stackTmax);
+                } else if (wantLeaf) {
+                    leaf_step<SOA, PACKED>(s, st, o, d, any, clip, hit, found, stackNode, stackTmin, stackTmax);
+                }
+            } else {
+                ++nodeRun;
+                if (wantNode) {
+                    node_step(s, st, o, d, clip, stackNode, stackTmin, stackTmax);
+                }
+            }
+            if (DONATE && --budget == 0u) {
+                break;
+            }
+        }
+        if (!DONATE || finished) {
             break;
         }
-        const uint32_t nLeaf = __popc(leafMask), nNode = __popc(nodeMask);
-        if (nNode == 0u || (nLeaf != 0u && (nLeaf * s.tune[1] >= nNode * s.tune[0] || nodeRun >= s.tune[2]))) {
-            nodeRun = 0;
-            if (SHARE && nLeaf <= 4u) {
-                leaf_step_coop(s, st, leafMask, nLeaf, wantLeaf, o, d, any, clip, hit, found, stackNode, stackTmin,
-                               stackTmax);
-            } else if (wantLeaf) {
-                leaf_step<SOA, PACKED>(s, st, o, d, any, clip, hit, found, stackNode, stackTmin, stackTmax);
-            }
-        } else {
-            ++nodeRun;
-            if (wantNode) {
-                node_step(s, st, o, d, clip, stackNode, stackTmin, stackTmax);
-            }
+        // do idle warps wait for rays?
+        const uint32_t want = p->donate_slots != nullptr ? donate_poll(*p) : 0u;
+        if (want != 0u) {
+            donate_live_rays(*p, want, st, o, d, any, clip, hit, found, fin, stackNode, stackTmin, stackTmax, *donated);
         }
     }
     return found;
@@ -400,11 +424,15 @@ __device__ __forceinline__ bool analytic_chain(const DeviceScene &s, uint32_t cl
 
 // One full query for this thread's ray.  `valid` = the thread has a ray at all; in the voted variant every
 // lane of the warp must call this (the traversal is warp-synchronous).
+// `p`, `kind`, `out` (variant 7 only): how the ray's result is written, so that a ray suspended into the donation
+// queue can be finished by another warp; `*donated` is set when that happened (the caller must not write).
 template <int VARIANT>
 __device__ __forceinline__ bool query(const DeviceScene &s, uint32_t classes, bool valid, const float o[3],
-                                      const float d[3], bool any, float clip, Hit &hit)
+                                      const float d[3], bool any, float clip, Hit &hit, const TraceParams *p = nullptr,
+                                      uint32_t kind = 0, uint64_t out = 0, bool *donated = nullptr)
 {
     bool found = false;
+    const float clip0 = clip;
     hit.t = clip;
     hit.prim = DODRT_MISS;
     hit.u = hit.v = 0.0f;
@@ -414,8 +442,21 @@ __device__ __forceinline__ bool query(const DeviceScene &s, uint32_t classes, bo
     }
     const bool enter = !decided && (classes & DODRT_CLS_TREE);
     Hit h;
-    if (VARIANT >= 2) {
-        if (kdtree_query_voted<VARIANT >= 3, VARIANT == 5, VARIANT == 6>(s, enter, o, d, any, clip, h)) {
+    if (VARIANT == kDonateVariant) {
+        Finish fin;
+        fin.out = out;
+        fin.kind = kind;
+        fin.pre[0] = kind == kFinishAnyRecord ? clip0 : hit.t;
+        fin.pre[1] = __uint_as_float(hit.prim);
+        fin.pre[2] = hit.u;
+        fin.pre[3] = hit.v;
+        h.t = clip, h.prim = DODRT_MISS, h.u = h.v = 0.0f;
+        if (kdtree_query_voted<true, false, false, true>(s, enter, o, d, any, clip, h, p, &fin, donated)) {
+            hit = h;
+            found = true;
+        }
+    } else if (VARIANT >= 2) {
+        if (kdtree_query_voted<VARIANT >= 3, VARIANT == 5, VARIANT == 6, false>(s, enter, o, d, any, clip, h)) {
             hit = h;
             found = true;
         }
@@ -504,7 +545,8 @@ template <int MODE> __global__ void order_tiles_kernel(const TraceParams p)
 #ifndef DODRT_MINBLOCKS
 #define DODRT_MINBLOCKS 1
 #endif
-template <int MODE, int VARIANT> __global__ void __launch_bounds__(128, DODRT_MINBLOCKS) trace_kernel(const TraceParams p)
+template <int MODE, int VARIANT>
+__global__ void __launch_bounds__(128, VARIANT == kDonateVariant ? 5 : DODRT_MINBLOCKS) trace_kernel(const TraceParams p)
 {
     const uint32_t lane = threadIdx.x & 31u;
     for (;;) {
@@ -534,8 +576,9 @@ template <int MODE, int VARIANT> __global__ void __launch_bounds__(128, DODRT_MI
                 }
             }
             Hit h;
-            const bool blocked = query<VARIANT>(p.scene, p.classes, cast, so, sd, true, sclip, h);
-            if (inRange) {
+            bool donated = false;
+            const bool blocked = query<VARIANT>(p.scene, p.classes, cast, so, sd, true, sclip, h, &p, kFinishVisible, item, &donated);
+            if (inRange && !donated) {
                 p.visible[item] = (cast && !blocked) ? 1 : 0;
             }
         } else if (MODE == kModeRays) {
@@ -552,8 +595,10 @@ template <int MODE, int VARIANT> __global__ void __launch_bounds__(128, DODRT_MI
                 skip = (__float_as_uint(b.w) & DODRT_RAY_SKIP) != 0u;
             }
             Hit h;
-            const bool found = query<VARIANT>(p.scene, p.classes, inRange && !skip, o, d, any, clip, h);
-            if (inRange) {
+            bool donated = false;
+            const bool found = query<VARIANT>(p.scene, p.classes, inRange && !skip, o, d, any, clip, h, &p,
+                                              any ? kFinishAnyRecord : kFinishRecord, item, &donated);
+            if (inRange && !donated) {
                 if (any) { // any-hit defines only hit/miss
                     h.t = clip;
                     h.prim = found ? 0u : DODRT_MISS;
@@ -573,8 +618,9 @@ template <int MODE, int VARIANT> __global__ void __launch_bounds__(128, DODRT_MI
             }
             if (MODE == kModePrimary) {
                 Hit h;
-                query<VARIANT>(p.scene, p.classes, inside, o, d, false, kInfinity, h);
-                if (inside || (inRange && p.frame.compact)) { // padded slots of edge tiles read as "miss"
+                bool donated = false;
+                query<VARIANT>(p.scene, p.classes, inside, o, d, false, kInfinity, h, &p, kFinishRecord, out, &donated);
+                if ((inside || (inRange && p.frame.compact)) && !donated) { // padded slots of edge tiles read as "miss"
                     reinterpret_cast<float4 *>(p.hits)[out] = make_float4(h.t, __uint_as_float(h.prim), h.u, h.v);
                 }
             } else {
@@ -588,14 +634,21 @@ template <int MODE, int VARIANT> __global__ void __launch_bounds__(128, DODRT_MI
                     }
                 }
                 Hit h;
-                const bool blocked = query<VARIANT>(p.scene, p.classes, cast, so, sd, true, sclip, h);
+                bool donated = false;
+                const bool blocked = query<VARIANT>(p.scene, p.classes, cast, so, sd, true, sclip, h, &p, kFinishVisible, out,
+                                                    &donated);
                 shadowed = !cast || blocked;
-                if (inside || (inRange && p.frame.compact)) {
+                if ((inside || (inRange && p.frame.compact)) && !donated) {
                     p.visible[out] = shadowed ? 0 : 1;
                 }
             }
         }
     }
+#ifndef DBG_NOHELPER
+    if (VARIANT == kDonateVariant && p.donate_slots != nullptr) {
+        donate_helper_loop(p);
+    }
+#endif
 }
 
 #include "dodrt_pool_kernel.inl"
@@ -738,14 +791,36 @@ cudaError_t trace_launch_config(int device, TraceMode mode, int variant, LaunchC
     case 3: return config_mode<3>(device, mode, cfg);
     case 4: return config_mode<4>(device, mode, cfg);
     case 5: return config_mode<5>(device, mode, cfg);
-    default: return config_mode<6>(device, mode, cfg);
+    case 6: return config_mode<6>(device, mode, cfg);
+    default: return config_mode<7>(device, mode, cfg);
     }
 }
 
-cudaError_t launch_trace(TraceMode mode, const TraceParams &p, const LaunchConfig &cfg, cudaStream_t stream)
+cudaError_t launch_trace(TraceMode mode, const TraceParams &params, const LaunchConfig &cfg, cudaStream_t stream,
+                         cudaMemPool_t pool)
 {
+    TraceParams p = params;
     cudaError_t e = cudaMemsetAsync(p.counter, 0, sizeof(unsigned long long) * kCounterWords, stream);
     if (e != cudaSuccess) return e;
+    // variant 7: the donation queue lives for this launch only (stream-ordered allocation from the scene's pool);
+    // one slot per thread of the grid bounds the number of rays that can ever be suspended at once
+    p.donate_slots = p.donate_ready = nullptr;
+    p.donate_capacity = 0;
+    void *queue = nullptr;
+    static const bool donateOn = [] { const char *e = std::getenv("DODRT_DONATE"); return !e || std::atoi(e) != 0; }();
+    if (donateOn && p.variant == kDonateVariant && pool != nullptr && p.scene.num_nodes != 0 && (p.classes & DODRT_CLS_TREE)) {
+        // donors check `tail <= capacity / 2` before reserving; every warp of the grid can pass that check at the same
+        // time and reserve up to 32 slots, hence twice the grid's threads
+        const size_t cap = (size_t)cfg.grid * cfg.block * 2;
+        const size_t readyBytes = (cap * sizeof(uint32_t) + 255) & ~(size_t)255;
+        e = cudaMallocFromPoolAsync(&queue, readyBytes + cap * kDonateSlotWords * sizeof(uint32_t), pool, stream);
+        if (e != cudaSuccess) return e;
+        e = cudaMemsetAsync(queue, 0, readyBytes, stream);
+        if (e != cudaSuccess) return e;
+        p.donate_ready = static_cast<uint32_t *>(queue);
+        p.donate_slots = reinterpret_cast<uint32_t *>(static_cast<char *>(queue) + readyBytes);
+        p.donate_capacity = (uint32_t)cap;
+    }
     if (p.tile_order && (mode == kModePrimary || mode == kModeShadow)) {
         const unsigned blocks = (p.num_local_tiles + 127u) / 128u;
         if (mode == kModePrimary) {
@@ -761,9 +836,14 @@ cudaError_t launch_trace(TraceMode mode, const TraceParams &p, const LaunchConfi
     case 3: launch_mode<3>(mode, p, cfg, stream); break;
     case 4: launch_mode<4>(mode, p, cfg, stream); break;
     case 5: launch_mode<5>(mode, p, cfg, stream); break;
-    default: launch_mode<6>(mode, p, cfg, stream); break;
+    case 6: launch_mode<6>(mode, p, cfg, stream); break;
+    default: launch_mode<7>(mode, p, cfg, stream); break;
     }
-    return cudaGetLastError();
+    e = cudaGetLastError();
+    if (queue) {
+        cudaFreeAsync(queue, stream);
+    }
+    return e;
 }
 
 cudaError_t launch_assemble(const dodrt_frame &frame, uint32_t tiles_x, const dodrt_hit *compactHits,

@@ -12,7 +12,7 @@ enum TraceMode : int {
 };
 constexpr int kNumModes = 4;
 
-constexpr int kNumVariants = 7;    // see the header comment of dodrt_kernels.cu
+constexpr int kNumVariants = 8;    // see the header comment of dodrt_kernels.cu
 constexpr int kDefaultVariant = 3;
 int default_variant();             // kDefaultVariant unless env DODRT_VARIANT overrides it
 
@@ -39,9 +39,21 @@ struct TraceParams {
     // results still land in the natural slots.  nullptr = natural order.
     uint32_t *tile_order;
     uint32_t num_local_tiles;
+    // variant 7 (ray donation, dodrt_donate.inl): per-launch queue of suspended rays, filled by warps that are still
+    // working when others have run out of work; nullptr = donation off
+    uint32_t *donate_slots;   // donate_capacity x kDonateSlotWords words
+    uint32_t *donate_ready;   // donate_capacity flags, zeroed before the launch
+    uint32_t donate_capacity;
 };
 
-constexpr int kCounterWords = 4;
+// counters (one 256-B block per launch): [0] next work item, [1]/[2] heavy/light tiles placed (order_tiles_kernel);
+// on their own 128-B line, away from the work counter every warp hammers: [16] warps that left the main loop,
+// [17] donation tickets taken by helpers, [18] donation slots reserved by donors (dodrt_donate.inl)
+constexpr int kCounterWords = 32;
+constexpr int kDonateFinished = 16, kDonateHead = 17, kDonateTail = 18;
+constexpr int kDonateVariant = 7;
+constexpr int kDonateSlotWords = 80; // 24 header words + 16 stack entries x 3 + 8 spare = 320 B
+constexpr int kDonateMaxStack = 16;
 
 struct LaunchConfig {
     int grid;
@@ -50,7 +62,9 @@ struct LaunchConfig {
 
 // Occupancy-derived persistent launch shape for the given device (cached by the caller).
 cudaError_t trace_launch_config(int device, TraceMode mode, int variant, LaunchConfig *cfg);
-cudaError_t launch_trace(TraceMode mode, const TraceParams &p, const LaunchConfig &cfg, cudaStream_t stream);
+// `pool` (optional): stream-ordered pool the donation queue of variant 7 is taken from; nullptr = no donation
+cudaError_t launch_trace(TraceMode mode, const TraceParams &p, const LaunchConfig &cfg, cudaStream_t stream,
+                         cudaMemPool_t pool = nullptr);
 
 // ---- shading / bounce loop (dodrt_render_kernels.cu): rayTrace, main.cpp:273-347 ---------------------------------
 constexpr int kMaxLights = 16;

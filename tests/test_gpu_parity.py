@@ -21,7 +21,7 @@ def sha(a):
     return hashlib.sha256(np.ascontiguousarray(a).tobytes()).hexdigest()
 
 
-@pytest.fixture(scope="module", params=[0, 1, 2, 3, 4, 5, 6], ids=lambda v: f"variant{v}")
+@pytest.fixture(scope="module", params=[0, 1, 2, 3, 4, 5, 6, 7], ids=lambda v: f"variant{v}")
 def teapot(request):
     """every kernel variant must return the same bits"""
     scene = teapot_scene(full=True)
@@ -243,7 +243,7 @@ def test_full_reference_frame_pixels_within_one_255th():
     want = np.load(f"{GOLDEN}/teapot_render_240x135.npz")["rgb"].astype(np.int32)
     h, w = want.shape[:2]
     xs, ys = host.ray_tables(w, h)
-    for variant in (3, 0, 4, 6):
+    for variant in (3, 0, 4, 6, 7):
         with _render_scene().upload(0, shading=True) as g:
             g.set_kernel_variant(variant)
             got = g.render(capi.Frame.make(w, h, classes=ALL), xs, ys, workloads.REFERENCE_LIGHTS,
@@ -301,3 +301,36 @@ def test_gpu_side_lane_reorder_matches_host_reorder():
     assert out[0][1] == out[1][1], "visibility differs"
     assert out[0][2] == out[1][2], "rendered pixels differ"
     assert (np.frombuffer(out[0][0], capi.HIT_DT)["prim"] >> 29 == 0).sum() > 1000  # the teapot is in view
+
+
+def test_donated_rays_resume_bit_identically(monkeypatch, oracle):
+    """Variant 7 (dodrt_donate.inl).  DODRT_DONATE_ALWAYS makes every warp suspend its live rays at every poll, so
+    nearly every ray that traverses more than a few nodes is finished by the 32-lane resume path; all four finishers
+    (hit record, any-hit record, visibility byte of both shadow modes) must give the bits of the plain kernel."""
+    from dod_raytracer_b200 import host, workloads
+    scene = teapot_scene(full=True)
+    rays = oracle.primary_rays(480, 270)
+    anyrays = rays.copy()
+    anyrays["flags"] = RAY_ANY
+    anyrays["clip"] = 6.0
+    w, h = 640, 360
+    xs, ys = host.ray_tables(w, h)
+    frame = capi.Frame.make(w, h, classes=ALL)
+    results = []
+    for always in ("0", "1"):
+        monkeypatch.setenv("DODRT_DONATE_ALWAYS", always)
+        with upload(scene) as g:
+            g.set_kernel_variant(7 if always == "1" else 3)
+            hits, vis = g.trace_frame(frame, xs, ys, LIGHT0[None, :])
+            results.append((g.intersect(rays, ALL).tobytes(), g.intersect(anyrays, ALL).tobytes(), hits.tobytes(), vis.tobytes()))
+    for a, b, what in zip(results[0], results[1], ("closest", "any-hit", "frame hits", "frame visibility")):
+        assert a == b, what
+    monkeypatch.setenv("DODRT_DONATE_ALWAYS", "1")
+    with _render_scene().upload(0, shading=True) as g:  # kModeShadowRays finisher (bounce loop)
+        g.set_kernel_variant(7)
+        got = g.render(capi.Frame.make(160, 90, classes=ALL), *host.ray_tables(160, 90), workloads.REFERENCE_LIGHTS, 4)
+    monkeypatch.setenv("DODRT_DONATE_ALWAYS", "0")
+    with _render_scene().upload(0, shading=True) as g:
+        g.set_kernel_variant(3)
+        want = g.render(capi.Frame.make(160, 90, classes=ALL), *host.ray_tables(160, 90), workloads.REFERENCE_LIGHTS, 4)
+    assert got.tobytes() == want.tobytes()
