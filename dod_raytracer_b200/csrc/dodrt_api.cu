@@ -91,7 +91,7 @@ struct dodrt_scene {
     std::atomic<uint32_t> nextCounter{0};
     std::atomic<uint64_t> launches{0};
     LaunchConfig cfg[kNumVariants][kNumModes]{};
-    int variant = kDefaultVariant;
+    int variant = kVariantAuto; // kVariantAuto or an explicit variant (dodrt_scene_set_kernel_variant / DODRT_VARIANT)
     uint32_t treeDepth = 0;
     std::mutex mutex; // guards scene mutation and the lazily created staging stream
     cudaStream_t stream = nullptr;
@@ -238,7 +238,7 @@ int launchFrame(dodrt_scene *s, TraceMode mode, const dodrt_frame *frame, const 
         p.light[2] = light[2];
     }
     p.counter = nextCounter(s);
-    p.variant = s->variant;
+    p.variant = resolve_variant(s->variant, s->cfg[kDonateVariant][mode], p.count);
     if (p.count == 0) {
         return DODRT_OK;
     }
@@ -660,7 +660,7 @@ int dodrt_intersect_device(dodrt_scene *s, const dodrt_ray *d_rays, uint64_t num
     p.count = num_rays;
     p.hits = d_hits;
     p.counter = nextCounter(s);
-    p.variant = s->variant;
+    p.variant = resolve_variant(s->variant, s->cfg[kDonateVariant][kModeRays], p.count);
     p.tile_order = nullptr;
     p.num_local_tiles = 0;
     if (p.variant == kDonateVariant) {
@@ -956,7 +956,7 @@ int dodrt_render(dodrt_scene *s, const dodrt_frame *frame, const float *xs, cons
         p.rays = rp.rays;
         p.count = n;
         p.hits = rp.hits;
-        p.variant = s->variant;
+        p.variant = resolve_variant(s->variant, s->cfg[kDonateVariant][kModeRays], p.count);
         p.counter = nextCounter(s);
         e = launch_trace(kModeRays, p, s->cfg[p.variant][kModeRays], st, s->pool); // closest-hit chain, main.cpp:314-321
         if (e == cudaSuccess) s->launches.fetch_add(1);

@@ -776,10 +776,25 @@ int default_variant()
 {
     static const int v = [] {
         const char *e = std::getenv("DODRT_VARIANT");
-        const int x = e ? std::atoi(e) : kDefaultVariant;
-        return (x >= 0 && x < kNumVariants) ? x : kDefaultVariant;
+        if (!e) return kVariantAuto;
+        const int x = std::atoi(e);
+        return (x >= 0 && x < kNumVariants) ? x : kVariantAuto;
     }();
     return v;
+}
+
+// kVariantAuto: the plain voted kernel (variant 3) for long passes, the donating one (variant 7) when a pass is only
+// a few batches per warp -- a GPU's share of a frame split over several GPUs, small frames, bounce passes -- where
+// the tail of the pass (its slowest warp) is a large part of it.  Measured on dragon4k (profiles/r01_donation.txt):
+// whole frame, 87 batches per warp: variant 3 4.36 ms vs 4.59 ms; half a frame (43): 2.61 vs 2.44; an eighth (11):
+// 1.12 vs 0.80 ms.
+int resolve_variant(int variant, const LaunchConfig &donateCfg, uint64_t count)
+{
+    if (variant != kVariantAuto) {
+        return variant;
+    }
+    const uint64_t threads = (uint64_t)donateCfg.grid * donateCfg.block;
+    return count < threads * kDonateBelowBatches ? kDonateVariant : kDefaultVariant;
 }
 
 cudaError_t trace_launch_config(int device, TraceMode mode, int variant, LaunchConfig *cfg)

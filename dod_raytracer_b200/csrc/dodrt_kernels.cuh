@@ -14,7 +14,8 @@ constexpr int kNumModes = 4;
 
 constexpr int kNumVariants = 8;    // see the header comment of dodrt_kernels.cu
 constexpr int kDefaultVariant = 3;
-int default_variant();             // kDefaultVariant unless env DODRT_VARIANT overrides it
+constexpr int kVariantAuto = -1;   // pick per launch, see resolve_variant
+int default_variant();             // kVariantAuto unless env DODRT_VARIANT names a variant
 
 struct TraceParams {
     DeviceScene scene;
@@ -54,6 +55,7 @@ constexpr int kDonateFinished = 16, kDonateHead = 17, kDonateTail = 18;
 constexpr int kDonateVariant = 7;
 constexpr int kDonateSlotWords = 80; // 24 header words + 16 stack entries x 3 + 8 spare = 320 B
 constexpr int kDonateMaxStack = 16;
+constexpr uint64_t kDonateBelowBatches = 64; // auto: donate when a pass has fewer 32-ray batches per warp than this
 
 struct LaunchConfig {
     int grid;
@@ -62,6 +64,7 @@ struct LaunchConfig {
 
 // Occupancy-derived persistent launch shape for the given device (cached by the caller).
 cudaError_t trace_launch_config(int device, TraceMode mode, int variant, LaunchConfig *cfg);
+int resolve_variant(int variant, const LaunchConfig &donateCfg, uint64_t count);
 // `pool` (optional): stream-ordered pool the donation queue of variant 7 is taken from; nullptr = no donation
 cudaError_t launch_trace(TraceMode mode, const TraceParams &p, const LaunchConfig &cfg, cudaStream_t stream,
                          cudaMemPool_t pool = nullptr);
