@@ -7,6 +7,7 @@
 #include "dodrt_kernels.cuh"
 #include "dodrt_prim_bvh.cuh"
 
+#include <algorithm>
 #include <atomic>
 #include <cmath>
 #include <cstdarg>
@@ -302,6 +303,9 @@ int dodrt_scene_create(int device, dodrt_scene **scene)
         if (t) std::sscanf(t, "%u,%u,%u", &a, &b, &c);
         s->dev.tune[0] = a, s->dev.tune[1] = b, s->dev.tune[2] = c;
         // test knob for variant 7: suspend rays at every poll, helpers or not (exercises the resume path everywhere)
+        const char *burst = std::getenv("DODRT_NODE_BURST");
+        // measured on dragon4k (profiles/r01_node_burst.txt): 1 -> 3779, 2 -> 4003, 4 -> 4115, 8 -> 4203, 64 -> 4286 Mrays/s
+        s->dev.node_burst = burst ? (uint32_t)std::max(1, std::atoi(burst)) : 0xFFFFFFFFu;
         const char *always = std::getenv("DODRT_DONATE_ALWAYS");
         s->dev.tune[3] = (always && std::atoi(always) != 0) ? 1u : 0u;
     }

@@ -58,6 +58,9 @@ struct DeviceScene {
     uint32_t tune[4];
     // (-0.0f, -0.0f): the addend that turns FFMA2 into an un-fusable packed multiply (see f2_mul)
     unsigned long long negzero2;
+    // kd node steps a ray may take per node phase of the voted loop: 1 = one step per vote; default unlimited = the
+    // ray walks on until it stands in a non-empty leaf (or is done), the others wait -- a vote costs about one step
+    uint32_t node_burst;
 };
 
 struct Hit {

@@ -367,6 +367,11 @@ __device__ __forceinline__ bool kdtree_query_voted(const DeviceScene &s, bool en
                 ++nodeRun;
                 if (wantNode) {
                     node_step(s, st, o, d, clip, stackNode, stackTmin, stackTmax);
+                    // a ray that is still between leaves may go on: the vote (two ballots, the phase rule) costs
+                    // about as much as a node step
+                    for (uint32_t k = 1; k < s.node_burst && st.live && !(st.triCur < st.triEnd); k++) {
+                        node_step(s, st, o, d, clip, stackNode, stackTmin, stackTmax);
+                    }
                 }
             }
             if (DONATE && --budget == 0u) {
