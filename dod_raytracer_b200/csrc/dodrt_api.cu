@@ -306,6 +306,8 @@ int dodrt_scene_create(int device, dodrt_scene **scene)
         const char *burst = std::getenv("DODRT_NODE_BURST");
         // measured on dragon4k (profiles/r01_node_burst.txt): 1 -> 3779, 2 -> 4003, 4 -> 4115, 8 -> 4203, 64 -> 4286 Mrays/s
         s->dev.node_burst = burst ? (uint32_t)std::max(1, std::atoi(burst)) : 0xFFFFFFFFu;
+        const char *poll = std::getenv("DODRT_DONATE_POLL");
+        s->dev.donate_poll = poll ? (uint32_t)std::max(1, std::atoi(poll)) : 32u;
         const char *always = std::getenv("DODRT_DONATE_ALWAYS");
         s->dev.tune[3] = (always && std::atoi(always) != 0) ? 1u : 0u;
     }

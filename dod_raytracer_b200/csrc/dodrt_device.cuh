@@ -61,6 +61,8 @@ struct DeviceScene {
     // kd node steps a ray may take per node phase of the voted loop: 1 = one step per vote; default unlimited = the
     // ray walks on until it stands in a non-empty leaf (or is done), the others wait -- a vote costs about one step
     uint32_t node_burst;
+    // variant 7: voted iterations between two polls of the donation queue
+    uint32_t donate_poll;
 };
 
 struct Hit {
@@ -258,6 +260,50 @@ __device__ __forceinline__ bool lane_half_test(const float4 *__restrict__ lane, 
     DODRT_SLOT(2, m2, z)
     DODRT_SLOT(3, m3, w)
 #undef DODRT_SLOT
+    return any;
+}
+
+// First stage of lane_half_test alone: bit k of the result = slot 4h+k may still be accepted.
+__device__ __forceinline__ uint32_t lane_half_mask(const float4 *__restrict__ lane, int h, const float o[3], const float d[3])
+{
+    const float4 Ax = __ldg(lane + 0 + h), Ay = __ldg(lane + 2 + h), Az = __ldg(lane + 4 + h);
+    const float4 Bx = __ldg(lane + 6 + h), By = __ldg(lane + 8 + h), Bz = __ldg(lane + 10 + h);
+    const float4 Cx = __ldg(lane + 12 + h), Cy = __ldg(lane + 14 + h), Cz = __ldg(lane + 16 + h);
+    const uint32_t m0 = triangle_may_hit(Ax.x, Ay.x, Az.x, Bx.x, By.x, Bz.x, Cx.x, Cy.x, Cz.x, o, d);
+    const uint32_t m1 = triangle_may_hit(Ax.y, Ay.y, Az.y, Bx.y, By.y, Bz.y, Cx.y, Cy.y, Cz.y, o, d);
+    const uint32_t m2 = triangle_may_hit(Ax.z, Ay.z, Az.z, Bx.z, By.z, Bz.z, Cx.z, Cy.z, Cz.z, o, d);
+    const uint32_t m3 = triangle_may_hit(Ax.w, Ay.w, Az.w, Bx.w, By.w, Bz.w, Cx.w, Cy.w, Cz.w, o, d);
+    return m0 | (m1 << 1) | (m2 << 2) | (m3 << 3);
+}
+
+// One whole lane (8 slots), variant 8: the branch-free first stage for both halves, then ONE copy of the exact
+// test in a loop over the surviving slots, lowest slot first (so the running clip evolves as in the reference's
+// slot loop, triangle.cpp:119-139).  A survivor's nine floats are re-read from the lane (L1 hits).  lane_half_test
+// inlines the exact test once per slot -- eight copies per lane, each executed whenever ANY ray of the warp has a
+// survivor in that slot (ncu: 17 % of the shadow pass at 4-7 active threads); here the loop runs max-over-rays
+// survivor-count times and the hot loop is ~500 SASS instructions shorter.
+__device__ __forceinline__ bool lane_test_compact(const float4 *__restrict__ lane, uint32_t firstId, const float o[3],
+                                                  const float d[3], float &clip, Hit &hit)
+{
+    uint32_t m = lane_half_mask(lane, 0, o, d) | (lane_half_mask(lane, 1, o, d) << 4);
+    bool any = false;
+    while (m != 0u) {
+        const uint32_t k = (uint32_t)__ffs((int)m) - 1u;
+        m &= m - 1u;
+        const float *base = reinterpret_cast<const float *>(lane) + k;
+        const float4 q0 = make_float4(__ldg(base), __ldg(base + 8), __ldg(base + 16), __ldg(base + 24));
+        const float4 q1 = make_float4(__ldg(base + 32), __ldg(base + 40), __ldg(base + 48), __ldg(base + 56));
+        const float4 q2 = make_float4(__ldg(base + 64), 0.0f, 0.0f, 0.0f);
+        float t, u, v;
+        if (triangle_test_fast(q0, q1, q2, o, d, clip, t, u, v)) {
+            clip = t;
+            hit.t = t;
+            hit.prim = (DODRT_KIND_TRIANGLE << DODRT_KIND_SHIFT) | (firstId + k);
+            hit.u = u;
+            hit.v = v;
+            any = true;
+        }
+    }
     return any;
 }
 

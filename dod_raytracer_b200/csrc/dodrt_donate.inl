@@ -6,7 +6,7 @@
 // work idle meanwhile (rank 0 of 8: 44 % busy in the primary pass).
 //
 // How: a warp that cannot claim another batch does not exit; it becomes a HELPER and waits on a global queue.
-// A warp still traversing polls (one volatile load every kDonatePoll voted iterations) whether helpers exist; if
+// A warp still traversing polls (one volatile load every DeviceScene::donate_poll voted iterations) whether helpers exist; if
 // they outnumber the queued rays it SUSPENDS its live rays -- ray, running clip, best hit, node / leaf cursor and
 // the short stack -- into the queue and goes on to become a helper itself.  A helper resumes ONE ray with the whole
 // warp: kd node steps are warp-uniform, a leaf is tested 32 triangle slots at a time and reduced with the
@@ -15,7 +15,6 @@
 // A suspended ray resumes exactly where it stopped: no node is visited twice, the order of events per ray is the
 // reference's (kdtree.cpp:263-361).  All blocks of the launch are co-resident (grid = one wave), so waiting on the
 // queue cannot deadlock; the pass ends when every warp has left the main loop and the queue is empty.
-constexpr uint32_t kDonatePoll = 32;
 enum FinishKind : uint32_t { kFinishRecord = 0, kFinishAnyRecord = 1, kFinishVisible = 2 };
 
 // What remains to be done with the kd-tree's answer for one ray (main.cpp:320-325 / 209-217 as the trace kernel

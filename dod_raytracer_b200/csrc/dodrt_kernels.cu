@@ -26,6 +26,7 @@
 //      the fp32 issue slots for the same bits.
 //   7  variant 3 plus ray donation at the tail of a pass (dodrt_donate.inl): warps that ran out of work resume,
 //      32 lanes wide, the rays suspended by warps that are still traversing.
+//   8  variant 3 with ONE copy of the exact triangle test, looped over the first stage's survivors (lane_test_compact).
 // Every variant computes identical results (parity tests run all of them).
 #include "dodrt_kernels.cuh"
 #include "dodrt_prim_bvh.cuh"
@@ -155,12 +156,15 @@ __device__ __forceinline__ void tree_pop(TreeState &st, const uint32_t *stackNod
 }
 
 // One triangle lane (8 consecutive slots, triangle.cpp:43-140) of the leaf this ray is in.
-template <bool SOA, bool PACKED>
+template <bool SOA, bool PACKED, bool COMPACT = false>
 __device__ __forceinline__ void leaf_step(const DeviceScene &s, TreeState &st, const float o[3], const float d[3], bool any,
                                           float &clip, Hit &hit, bool &found, const uint32_t *stackNode,
                                           const float *stackTmin, const float *stackTmax)
 {
-    if (PACKED) {
+    if (COMPACT) {
+        const float4 *lane = s.lanes4 + (size_t)(st.triCur >> 3) * 18;
+        if (lane_test_compact(lane, st.triCur, o, d, clip, hit)) found = true;
+    } else if (PACKED) {
         const float4 *lane = s.lanes4 + (size_t)(st.triCur >> 3) * 18;
         const f32x2 o2[3] = {f2_pack(o[0], o[0]), f2_pack(o[1], o[1]), f2_pack(o[2], o[2])};
         const f32x2 d2[3] = {f2_pack(d[0], d[0]), f2_pack(d[1], d[1]), f2_pack(d[2], d[2])};
@@ -327,7 +331,7 @@ __device__ __forceinline__ void leaf_step_coop(const DeviceScene &s, TreeState &
 
 #include "dodrt_donate.inl"
 
-template <bool SOA, bool SHARE, bool PACKED, bool DONATE>
+template <bool SOA, bool SHARE, bool PACKED, bool DONATE, bool COMPACT = false>
 __device__ __forceinline__ bool kdtree_query_voted(const DeviceScene &s, bool enter, const float o[3], const float d[3],
                                                    bool any, float &clip, Hit &hit, const TraceParams *p = nullptr,
                                                    const Finish *fin = nullptr, bool *donated = nullptr)
@@ -339,12 +343,12 @@ __device__ __forceinline__ bool kdtree_query_voted(const DeviceScene &s, bool en
     float stackTmax[kMaxStack];
     bool found = false;
     uint32_t nodeRun = 0;
-    // The voted loop proper contains no atomics, volatile loads or calls; with DONATE it is left every kDonatePoll
+    // The voted loop proper contains no atomics, volatile loads or calls; with DONATE it is left every s.donate_poll
     // iterations for the poll / suspension below and re-entered (ptxas puts a YIELD at the head of a loop that
     // contains the poll, which cost the shadow pass 17 %).
     for (;;) {
         bool finished = false;
-        uint32_t budget = kDonatePoll;
+        uint32_t budget = s.donate_poll;
         for (;;) {
             const bool wantLeaf = st.live && st.triCur < st.triEnd;
             const bool wantNode = st.live && !wantLeaf;
@@ -361,7 +365,7 @@ __device__ __forceinline__ bool kdtree_query_voted(const DeviceScene &s, bool en
                     leaf_step_coop(s, st, leafMask, nLeaf, wantLeaf, o, d, any, clip, hit, found, stackNode, stackTmin,
                                    stackTmax);
                 } else if (wantLeaf) {
-                    leaf_step<SOA, PACKED>(s, st, o, d, any, clip, hit, found, stackNode, stackTmin, stackTmax);
+                    leaf_step<SOA, PACKED, COMPACT>(s, st, o, d, any, clip, hit, found, stackNode, stackTmin, stackTmax);
                 }
             } else {
                 ++nodeRun;
@@ -461,7 +465,7 @@ __device__ __forceinline__ bool query(const DeviceScene &s, uint32_t classes, bo
             found = true;
         }
     } else if (VARIANT >= 2) {
-        if (kdtree_query_voted<VARIANT >= 3, VARIANT == 5, VARIANT == 6, false>(s, enter, o, d, any, clip, h)) {
+        if (kdtree_query_voted<VARIANT >= 3, VARIANT == 5, VARIANT == 6, false, VARIANT == 8>(s, enter, o, d, any, clip, h)) {
             hit = h;
             found = true;
         }
@@ -551,7 +555,7 @@ template <int MODE> __global__ void order_tiles_kernel(const TraceParams p)
 #define DODRT_MINBLOCKS 1
 #endif
 template <int MODE, int VARIANT>
-__global__ void __launch_bounds__(128, VARIANT == kDonateVariant ? 5 : DODRT_MINBLOCKS) trace_kernel(const TraceParams p)
+__global__ void __launch_bounds__(128, VARIANT >= kDonateVariant ? 5 : DODRT_MINBLOCKS) trace_kernel(const TraceParams p)
 {
     const uint32_t lane = threadIdx.x & 31u;
     for (;;) {
@@ -790,9 +794,9 @@ int default_variant()
 
 // kVariantAuto: the plain voted kernel (variant 3) for long passes, the donating one (variant 7) when a pass is only
 // a few batches per warp -- a GPU's share of a frame split over several GPUs, small frames, bounce passes -- where
-// the tail of the pass (its slowest warp) is a large part of it.  Measured on dragon4k (profiles/r01_donation.txt):
-// whole frame, 87 batches per warp: variant 3 4.36 ms vs 4.59 ms; half a frame (43): 2.61 vs 2.44; an eighth (11):
-// 1.12 vs 0.80 ms.
+// the tail of the pass (its slowest warp) is a large part of it.  Measured on dragon4k (profiles/r01_donation.txt),
+// max over ranks of primary + shadow kernel time, variant 3 vs 7: whole frame (87 batches per warp) 3.88 vs 4.40 ms;
+// half (43) 2.31 vs 2.38; a quarter (22) 1.48 vs 1.35; an eighth (11) 1.02 vs 0.82 ms.
 int resolve_variant(int variant, const LaunchConfig &donateCfg, uint64_t count)
 {
     if (variant != kVariantAuto) {
@@ -812,7 +816,8 @@ cudaError_t trace_launch_config(int device, TraceMode mode, int variant, LaunchC
     case 4: return config_mode<4>(device, mode, cfg);
     case 5: return config_mode<5>(device, mode, cfg);
     case 6: return config_mode<6>(device, mode, cfg);
-    default: return config_mode<7>(device, mode, cfg);
+    case 7: return config_mode<7>(device, mode, cfg);
+    default: return config_mode<8>(device, mode, cfg);
     }
 }
 
@@ -857,7 +862,8 @@ cudaError_t launch_trace(TraceMode mode, const TraceParams &params, const Launch
     case 4: launch_mode<4>(mode, p, cfg, stream); break;
     case 5: launch_mode<5>(mode, p, cfg, stream); break;
     case 6: launch_mode<6>(mode, p, cfg, stream); break;
-    default: launch_mode<7>(mode, p, cfg, stream); break;
+    case 7: launch_mode<7>(mode, p, cfg, stream); break;
+    default: launch_mode<8>(mode, p, cfg, stream); break;
     }
     e = cudaGetLastError();
     if (queue) {

@@ -12,7 +12,7 @@ enum TraceMode : int {
 };
 constexpr int kNumModes = 4;
 
-constexpr int kNumVariants = 8;    // see the header comment of dodrt_kernels.cu
+constexpr int kNumVariants = 9;    // see the header comment of dodrt_kernels.cu
 constexpr int kDefaultVariant = 3;
 constexpr int kVariantAuto = -1;   // pick per launch, see resolve_variant
 int default_variant();             // kVariantAuto unless env DODRT_VARIANT names a variant
@@ -55,7 +55,7 @@ constexpr int kDonateFinished = 16, kDonateHead = 17, kDonateTail = 18;
 constexpr int kDonateVariant = 7;
 constexpr int kDonateSlotWords = 80; // 24 header words + 16 stack entries x 3 + 8 spare = 320 B
 constexpr int kDonateMaxStack = 16;
-constexpr uint64_t kDonateBelowBatches = 64; // auto: donate when a pass has fewer 32-ray batches per warp than this
+constexpr uint64_t kDonateBelowBatches = 32; // auto: donate when a pass has fewer 32-ray batches per warp than this
 
 struct LaunchConfig {
     int grid;

@@ -21,7 +21,7 @@ def sha(a):
     return hashlib.sha256(np.ascontiguousarray(a).tobytes()).hexdigest()
 
 
-@pytest.fixture(scope="module", params=[0, 1, 2, 3, 4, 5, 6, 7], ids=lambda v: f"variant{v}")
+@pytest.fixture(scope="module", params=[0, 1, 2, 3, 4, 5, 6, 7, 8], ids=lambda v: f"variant{v}")
 def teapot(request):
     """every kernel variant must return the same bits"""
     scene = teapot_scene(full=True)
