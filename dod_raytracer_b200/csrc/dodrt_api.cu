@@ -308,6 +308,8 @@ int dodrt_scene_create(int device, dodrt_scene **scene)
         s->dev.node_burst = burst ? (uint32_t)std::max(1, std::atoi(burst)) : 0xFFFFFFFFu;
         const char *poll = std::getenv("DODRT_DONATE_POLL");
         s->dev.donate_poll = poll ? (uint32_t)std::max(1, std::atoi(poll)) : 32u;
+        const char *refill = std::getenv("DODRT_POOL_REFILL");
+        s->dev.pool_refill = refill ? (uint32_t)std::min(32, std::max(1, std::atoi(refill))) : 32u;
         const char *always = std::getenv("DODRT_DONATE_ALWAYS");
         s->dev.tune[3] = (always && std::atoi(always) != 0) ? 1u : 0u;
     }

@@ -63,6 +63,8 @@ struct DeviceScene {
     uint32_t node_burst;
     // variant 7: voted iterations between two polls of the donation queue
     uint32_t donate_poll;
+    // variant 4: idle lanes that send the warp back to top up its ray pool (32 = only when every ray is finished)
+    uint32_t pool_refill;
 };
 
 struct Hit {

@@ -11,13 +11,13 @@
 //           test; rays that do not need the kd-tree are finished here, the survivors are COMPACTED
 //           (ballot + popc prefix) into the warp's pool;
 //   stage B: idle lanes pull rays out of the pool and join the warp-voted traversal (node step vs triangle
-//           lane, majority wins); when >= kRefillAt lanes are idle again the warp goes back to top up.
+//           lane, the phase rule of kdtree_query_voted); when >= DeviceScene::pool_refill lanes are idle again the warp
+//           goes back to top up (default 32 = no refill in mid-flight, the best setting measured).
 // Per-ray order of events is exactly the reference's (kdtree.cpp:263-361); only which lane hosts a ray, and
 // when, changes -- results are bit-identical to every other variant.
 
 constexpr int kPoolCap = 96;     // entries per warp
 constexpr int kPoolWords = 13;   // odd stride: conflict-free when consecutive lanes touch consecutive entries
-constexpr int kRefillAt = 8;     // idle lanes that trigger a top-up
 constexpr int kWarpsPerBlock = 4;
 
 struct PoolRay {
@@ -218,6 +218,7 @@ template <int MODE> __global__ void __launch_bounds__(32 * kWarpsPerBlock) trace
 
         // ---- stage B: voted traversal until enough lanes are idle to make a top-up worthwhile -----------------------
         bool anyLive = false;
+        uint32_t nodeRun = 0;
         for (;;) {
             const bool wantLeaf = st.live && st.triCur < st.triEnd;
             const bool wantNode = st.live && !wantLeaf;
@@ -228,15 +229,24 @@ template <int MODE> __global__ void __launch_bounds__(32 * kWarpsPerBlock) trace
             if (!anyLive) {
                 break;
             }
-            if (32 - nLive >= kRefillAt && (poolCount > 0 || !exhausted)) {
+            if (32 - nLive >= (int)s.pool_refill && (poolCount > 0 || !exhausted)) {
                 break;
             }
-            if (__popc(leafMask) >= __popc(nodeMask)) {
+            // same phase rule and node bursts as kdtree_query_voted
+            const uint32_t nLeaf = __popc(leafMask), nNode = __popc(nodeMask);
+            if (nNode == 0u || (nLeaf != 0u && (nLeaf * s.tune[1] >= nNode * s.tune[0] || nodeRun >= s.tune[2]))) {
+                nodeRun = 0;
                 if (wantLeaf) {
                     leaf_step<true, false>(s, st, o, d, any, clip, hit, found, stackNode, stackTmin, stackTmax);
                 }
-            } else if (wantNode) {
-                node_step(s, st, o, d, clip, stackNode, stackTmin, stackTmax);
+            } else {
+                ++nodeRun;
+                if (wantNode) {
+                    node_step(s, st, o, d, clip, stackNode, stackTmin, stackTmax);
+                    for (uint32_t k = 1; k < s.node_burst && st.live && !(st.triCur < st.triEnd); k++) {
+                        node_step(s, st, o, d, clip, stackNode, stackTmin, stackTmax);
+                    }
+                }
             }
         }
         if (!anyLive && exhausted && poolCount == 0) {
