@@ -239,7 +239,7 @@ int launchFrame(dodrt_scene *s, TraceMode mode, const dodrt_frame *frame, const 
         p.light[2] = light[2];
     }
     p.counter = nextCounter(s);
-    p.variant = resolve_variant(s->variant, s->cfg[kDonateVariant][mode], p.count);
+    p.variant = resolve_variant(s->variant, s->cfg[kDonateVariant][mode], p.count, frame->tile_stride > 1);
     if (p.count == 0) {
         return DODRT_OK;
     }
@@ -668,7 +668,7 @@ int dodrt_intersect_device(dodrt_scene *s, const dodrt_ray *d_rays, uint64_t num
     p.count = num_rays;
     p.hits = d_hits;
     p.counter = nextCounter(s);
-    p.variant = resolve_variant(s->variant, s->cfg[kDonateVariant][kModeRays], p.count);
+    p.variant = resolve_variant(s->variant, s->cfg[kDonateVariant][kModeRays], p.count, false);
     p.tile_order = nullptr;
     p.num_local_tiles = 0;
     if (p.variant == kDonateVariant) {
@@ -964,7 +964,8 @@ int dodrt_render(dodrt_scene *s, const dodrt_frame *frame, const float *xs, cons
         p.rays = rp.rays;
         p.count = n;
         p.hits = rp.hits;
-        p.variant = resolve_variant(s->variant, s->cfg[kDonateVariant][kModeRays], p.count);
+        // bounce passes: incoherent rays, long tails (dragon as-is frame 182 -> 166 ms with donation)
+        p.variant = resolve_variant(s->variant, s->cfg[kDonateVariant][kModeRays], p.count, true);
         p.counter = nextCounter(s);
         e = launch_trace(kModeRays, p, s->cfg[p.variant][kModeRays], st, s->pool); // closest-hit chain, main.cpp:314-321
         if (e == cudaSuccess) s->launches.fetch_add(1);
