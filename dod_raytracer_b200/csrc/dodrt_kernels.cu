@@ -796,9 +796,9 @@ int default_variant()
 // (`split`: a frame whose tiles are dealt over several GPUs, or a bounce pass of dodrt_render) and is only a few batches
 // per warp -- there the tail of the pass (its slowest warp) is a large part of it and the donating kernel (variant 7)
 // wins.  Measured on dragon4k (profiles/r01_donation.txt), max over ranks of primary + shadow kernel time, variant 3 vs
-// 7: whole frame (87 batches per warp) 3.88 vs 4.40 ms; half (43) 2.31 vs 2.38; a quarter (22) 1.48 vs 1.35; an eighth
-// (11) 1.02 vs 0.82 ms.  Whole small frames do not qualify: teapot1080 (22 batches per warp, short rays) 1.02 ms plain
-// vs 1.15 ms donating.
+// 7: whole frame (87 batches per warp) 3.79 vs 3.89 ms; half (43) 2.31 vs 2.11; a quarter (22) 1.48 vs 1.18; an eighth
+// (11) 1.02 vs 0.74 ms.  Whole small frames do not qualify: teapot1080 (22 batches per warp, short rays) 0.94 ms plain
+// vs 0.99 ms donating.
 int resolve_variant(int variant, const LaunchConfig &donateCfg, uint64_t count, bool split)
 {
     if (variant != kVariantAuto) {

@@ -55,7 +55,7 @@ constexpr int kDonateFinished = 16, kDonateHead = 17, kDonateTail = 18;
 constexpr int kDonateVariant = 7;
 constexpr int kDonateSlotWords = 80; // 24 header words + 16 stack entries x 3 + 8 spare = 320 B
 constexpr int kDonateMaxStack = 16;
-constexpr uint64_t kDonateBelowBatches = 32; // auto: donate when a pass has fewer 32-ray batches per warp than this
+constexpr uint64_t kDonateBelowBatches = 64; // auto: donate when a pass has fewer 32-ray batches per warp than this
 
 struct LaunchConfig {
     int grid;
