@@ -239,7 +239,7 @@ int launchFrame(dodrt_scene *s, TraceMode mode, const dodrt_frame *frame, const 
         p.light[2] = light[2];
     }
     p.counter = nextCounter(s);
-    p.variant = resolve_variant(s->variant, s->cfg[kDonateVariant][mode], p.count, frame->tile_stride > 1);
+    p.variant = resolve_variant(s->variant, s->cfg[kDonateVariant][mode], p.count, frame->tile_stride > 1, s->dev.num_nodes >= kBigTreeNodes);
     if (p.count == 0) {
         return DODRT_OK;
     }
@@ -668,7 +668,7 @@ int dodrt_intersect_device(dodrt_scene *s, const dodrt_ray *d_rays, uint64_t num
     p.count = num_rays;
     p.hits = d_hits;
     p.counter = nextCounter(s);
-    p.variant = resolve_variant(s->variant, s->cfg[kDonateVariant][kModeRays], p.count, false);
+    p.variant = resolve_variant(s->variant, s->cfg[kDonateVariant][kModeRays], p.count, false, s->dev.num_nodes >= kBigTreeNodes);
     p.tile_order = nullptr;
     p.num_local_tiles = 0;
     if (p.variant == kDonateVariant) {
@@ -965,7 +965,7 @@ int dodrt_render(dodrt_scene *s, const dodrt_frame *frame, const float *xs, cons
         p.count = n;
         p.hits = rp.hits;
         // bounce passes: incoherent rays, long tails (dragon as-is frame 182 -> 166 ms with donation)
-        p.variant = resolve_variant(s->variant, s->cfg[kDonateVariant][kModeRays], p.count, true);
+        p.variant = resolve_variant(s->variant, s->cfg[kDonateVariant][kModeRays], p.count, true, s->dev.num_nodes >= kBigTreeNodes);
         p.counter = nextCounter(s);
         e = launch_trace(kModeRays, p, s->cfg[p.variant][kModeRays], st, s->pool); // closest-hit chain, main.cpp:314-321
         if (e == cudaSuccess) s->launches.fetch_add(1);

@@ -798,14 +798,15 @@ int default_variant()
 // wins.  Measured on dragon4k (profiles/r01_donation.txt), max over ranks of primary + shadow kernel time, variant 3 vs
 // 7: whole frame (87 batches per warp) 3.79 vs 3.89 ms; half (43) 2.31 vs 2.11; a quarter (22) 1.48 vs 1.18; an eighth
 // (11) 1.02 vs 0.74 ms.  Whole small frames do not qualify: teapot1080 (22 batches per warp, short rays) 0.94 ms plain
-// vs 0.99 ms donating.
-int resolve_variant(int variant, const LaunchConfig &donateCfg, uint64_t count, bool split)
+// vs 0.99 ms donating -- but a small frame over a BIG tree does (`bigTree`, >= 8192 kd nodes: rays are long, the pass
+// is mostly tail): dragon1080_primary 0.51 ms plain vs 0.34 ms donating.
+int resolve_variant(int variant, const LaunchConfig &donateCfg, uint64_t count, bool split, bool bigTree)
 {
     if (variant != kVariantAuto) {
         return variant;
     }
     const uint64_t threads = (uint64_t)donateCfg.grid * donateCfg.block;
-    return (split && count < threads * kDonateBelowBatches) ? kDonateVariant : kDefaultVariant;
+    return ((split || bigTree) && count < threads * kDonateBelowBatches) ? kDonateVariant : kDefaultVariant;
 }
 
 cudaError_t trace_launch_config(int device, TraceMode mode, int variant, LaunchConfig *cfg)

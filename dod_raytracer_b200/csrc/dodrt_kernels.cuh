@@ -64,7 +64,8 @@ struct LaunchConfig {
 
 // Occupancy-derived persistent launch shape for the given device (cached by the caller).
 cudaError_t trace_launch_config(int device, TraceMode mode, int variant, LaunchConfig *cfg);
-int resolve_variant(int variant, const LaunchConfig &donateCfg, uint64_t count, bool split);
+int resolve_variant(int variant, const LaunchConfig &donateCfg, uint64_t count, bool split, bool bigTree);
+constexpr uint32_t kBigTreeNodes = 8192;
 // `pool` (optional): stream-ordered pool the donation queue of variant 7 is taken from; nullptr = no donation
 cudaError_t launch_trace(TraceMode mode, const TraceParams &p, const LaunchConfig &cfg, cudaStream_t stream,
                          cudaMemPool_t pool = nullptr);
