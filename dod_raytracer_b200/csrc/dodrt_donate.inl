@@ -13,8 +13,11 @@
 // lexicographic (t, slot) minimum, which is what the reference's slot-by-slot loop with its strict `<` leaves behind
 // (triangle.cpp:119-139) -- the same reduction as leaf_step_coop, bit-identical to every other variant.
 // A suspended ray resumes exactly where it stopped: no node is visited twice, the order of events per ray is the
-// reference's (kdtree.cpp:263-361).  All blocks of the launch are co-resident (grid = one wave), so waiting on the
-// queue cannot deadlock; the pass ends when every warp has left the main loop and the queue is empty.
+// reference's (kdtree.cpp:263-361).  Helpers wait only for warps that have ENTERED the kernel (counted at entry), never
+// for the grid size: if the SMs are shared with another kernel -- e.g. a second donating launch on another stream -- some
+// blocks may not be resident yet, and they could never start while everybody spins.  A block that starts late finds
+// the work counter exhausted and has nothing to donate, so the pass ends when every warp that entered has left its
+// main loop and the queue is drained (tests/test_gpu_parity.py::test_concurrent_donating_launches).
 enum FinishKind : uint32_t { kFinishRecord = 0, kFinishAnyRecord = 1, kFinishVisible = 2 };
 
 // What remains to be done with the kd-tree's answer for one ray (main.cpp:320-325 / 209-217 as the trace kernel
@@ -229,7 +232,6 @@ __device__ __forceinline__ void resume_ray(const TraceParams &p, uint32_t slot)
 __device__ __forceinline__ void donate_helper_loop(const TraceParams &p)
 {
     const uint32_t lane = threadIdx.x & 31u;
-    const unsigned long long totalWarps = (unsigned long long)gridDim.x * (blockDim.x >> 5);
     if (lane == 0) {
         __threadfence(); // this warp's donations (if any) are published before it counts as finished
         atomicAdd(p.counter + kDonateFinished, 1ull);
@@ -251,9 +253,17 @@ __device__ __forceinline__ void donate_helper_loop(const TraceParams &p)
                     ready = 1;
                     break;
                 }
-                if (ld_volatile_u64(p.counter + kDonateFinished) == totalWarps) {
-                    // no donor is left: slots below tail are filled or being filled by warps that counted as finished
-                    // only after publishing them, so tail is final here
+                // "No donor is left" = every warp that ENTERED the kernel has left its main loop.  Warps are counted
+                // when they enter (trace_kernel), not taken from the grid size: blocks that are not resident yet --
+                // the SMs may be shared with another kernel, e.g. a second donating launch on another stream -- must
+                // not be waited for (they could never start while everybody spins here).  A warp that starts later
+                // finds the work counter exhausted (a helper exists only once it is), so it never donates.
+                // finished <= started at all times and both only grow: reading finished first, equal values mean
+                // that all warps started by then had finished by then.
+                const unsigned long long done = ld_volatile_u64(p.counter + kDonateFinished);
+                if (done == ld_volatile_u64(p.counter + kDonateStarted)) {
+                    // slots below tail are filled or being filled by warps that counted as finished only after
+                    // publishing them, so tail is final here
                     __threadfence();
                     if (ld_volatile_u64(p.counter + kDonateTail) <= ticket) {
                         break;

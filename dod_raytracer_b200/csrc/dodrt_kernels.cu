@@ -558,6 +558,9 @@ template <int MODE, int VARIANT>
 __global__ void __launch_bounds__(128, VARIANT >= kDonateVariant ? 5 : DODRT_MINBLOCKS) trace_kernel(const TraceParams p)
 {
     const uint32_t lane = threadIdx.x & 31u;
+    if (VARIANT == kDonateVariant && p.donate_slots != nullptr && lane == 0) {
+        atomicAdd(p.counter + kDonateStarted, 1ull); // see donate_helper_loop
+    }
     for (;;) {
         unsigned long long base = 0;
         if (lane == 0) {

@@ -49,9 +49,10 @@ struct TraceParams {
 
 // counters (one 256-B block per launch): [0] next work item, [1]/[2] heavy/light tiles placed (order_tiles_kernel);
 // on their own 128-B line, away from the work counter every warp hammers: [16] warps that left the main loop,
-// [17] donation tickets taken by helpers, [18] donation slots reserved by donors (dodrt_donate.inl)
+// [17] donation tickets taken by helpers, [18] donation slots reserved by donors, [19] warps that entered the kernel
+// (dodrt_donate.inl)
 constexpr int kCounterWords = 32;
-constexpr int kDonateFinished = 16, kDonateHead = 17, kDonateTail = 18;
+constexpr int kDonateFinished = 16, kDonateHead = 17, kDonateTail = 18, kDonateStarted = 19;
 constexpr int kDonateVariant = 7;
 constexpr int kDonateSlotWords = 80; // 24 header words + 16 stack entries x 3 + 8 spare = 320 B
 constexpr int kDonateMaxStack = 16;

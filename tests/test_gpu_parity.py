@@ -334,3 +334,50 @@ def test_donated_rays_resume_bit_identically(monkeypatch, oracle):
         g.set_kernel_variant(3)
         want = g.render(capi.Frame.make(160, 90, classes=ALL), *host.ray_tables(160, 90), workloads.REFERENCE_LIGHTS, 4)
     assert got.tobytes() == want.tobytes()
+
+
+def test_concurrent_donating_launches(oracle):
+    """Four host threads trace frames with the donating kernel (variant 7) at the same time, each on its own CUDA
+    stream: the grids together exceed what the GPU can keep resident, so blocks of one launch start only when blocks
+    of another retire.  The helper loop must not wait for blocks that have not started (it counts warps at kernel
+    entry); every call has to return, with the single-launch bits."""
+    import threading
+    import torch
+    from dod_raytracer_b200 import host
+    scene = teapot_scene(full=True)
+    w, h = 512, 288
+    xs, ys = host.ray_tables(w, h)
+    frame = capi.Frame.make(w, h, classes=ALL)
+    dev = torch.device("cuda:0")
+    d_xs, d_ys = torch.from_numpy(xs).to(dev), torch.from_numpy(ys).to(dev)
+    light = np.asarray(LIGHT0, np.float32)
+    with upload(scene) as g:
+        g.set_kernel_variant(7)
+        want_hits, want_vis = g.trace_frame(frame, xs, ys, LIGHT0[None, :])
+        results, errors = {}, []
+
+        def work(k):
+            try:
+                st = torch.cuda.Stream(device=dev)
+                d_hits = torch.empty((w * h, 16), dtype=torch.uint8, device=dev)
+                d_vis = torch.empty(w * h, dtype=torch.uint8, device=dev)
+                for rep in range(8):
+                    g.trace_primary_device(frame, d_xs.data_ptr(), d_ys.data_ptr(), d_hits.data_ptr(), st.cuda_stream)
+                    g.trace_shadow_device(frame, d_xs.data_ptr(), d_ys.data_ptr(), d_hits.data_ptr(), light, d_vis.data_ptr(),
+                                          st.cuda_stream)
+                st.synchronize()
+                results[k] = (d_hits.cpu().numpy().tobytes(), d_vis.cpu().numpy().tobytes())
+            except Exception as e:  # noqa: BLE001
+                errors.append(e)
+
+        threads = [threading.Thread(target=work, args=(k,), daemon=True) for k in range(4)]
+        for t in threads:
+            t.start()
+        for t in threads:
+            t.join(timeout=120)
+            assert not t.is_alive(), "a donating launch did not return (helpers waiting for non-resident blocks?)"
+        assert not errors, errors
+        assert len(results) == 4
+        for k, (hits, vis) in results.items():
+            assert hits == want_hits.tobytes(), k
+            assert vis == want_vis[0].tobytes(), k
