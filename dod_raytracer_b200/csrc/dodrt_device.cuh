@@ -424,7 +424,11 @@ __device__ __forceinline__ bool lane_half_test_packed(const float4 *__restrict__
     return any;
 }
 
-// Sphere::intersect_impl, sphere.cpp:26-160 (lane-structured for the any-hit break, sphere.cpp:138-141)
+// Sphere::intersect_impl, sphere.cpp:26-160 (lane-structured for the any-hit break, sphere.cpp:138-141).
+// Four spheres at a time: the cheap part of the reference's sequence (L, distSq, tca, d2 and its two rejections,
+// sphere.cpp:62-90) runs branch-free for all four -- independent dependency chains, no divergence -- and only spheres
+// that pass it take the sqrt and the t0/t1 tests, in slot order.  Same operations on the same operands as the
+// slot-by-slot loop, so every accepted distance has the same bits.
 __device__ __forceinline__ bool sphere_query(const DeviceScene &s, const float o[3], const float d[3], bool any,
                                              float clip, Hit &hit)
 {
@@ -440,37 +444,40 @@ __device__ __forceinline__ bool sphere_query(const DeviceScene &s, const float o
             const float4 X = __ldg(lane + 0 + h), Y = __ldg(lane + 2 + h), Z = __ldg(lane + 4 + h), R = __ldg(lane + 6 + h);
             const float xs[4] = {X.x, X.y, X.z, X.w}, ys[4] = {Y.x, Y.y, Y.z, Y.w};
             const float zs[4] = {Z.x, Z.y, Z.z, Z.w}, rs[4] = {R.x, R.y, R.z, R.w};
+            float tca[4], d2[4];
+            bool ok[4];
 #pragma unroll
             for (int k = 0; k < 4; k++) {
                 const uint32_t j = h * 4 + k;
-                if (i * kLane + j >= s.num_spheres) {
-                    continue; // last-lane mask, sphere.cpp:31-37,46-49
-                }
                 float lx = xs[k] - o[0];
                 float ly = ys[k] - o[1];
                 float lz = zs[k] - o[2];
                 float distSq = dot3(lx, ly, lz, lx, ly, lz);
-                float radSq = rs[k];
-                if (!(distSq > radSq)) {
+                tca[k] = dot3(lx, ly, lz, d[0], d[1], d[2]);
+                float tcaSq = tca[k] * tca[k];
+                d2[k] = distSq - tcaSq;
+                // last-lane mask (sphere.cpp:31-37,46-49), origin outside (sphere.cpp:70), line within the radius (:88)
+                ok[k] = (i * kLane + j < s.num_spheres) & (distSq > rs[k]) & (d2[k] < rs[k]);
+            }
+            if (!(ok[0] | ok[1] | ok[2] | ok[3])) {
+                continue;
+            }
+#pragma unroll
+            for (int k = 0; k < 4; k++) {
+                if (!ok[k]) {
                     continue;
                 }
-                float tca = dot3(lx, ly, lz, d[0], d[1], d[2]);
-                float tcaSq = tca * tca;
-                float d2 = distSq - tcaSq;
-                if (!(d2 < radSq)) {
-                    continue;
-                }
-                float thcSq = radSq - d2;
+                float thcSq = rs[k] - d2[k];
                 float thc = sqrtf(thcSq);
-                float t0 = tca - thc;
-                float t1 = tca + thc;
+                float t0 = tca[k] - thc;
+                float t1 = tca[k] + thc;
                 if (!(t0 >= 0.0f && t1 >= 0.0f)) {
                     continue;
                 }
                 float tm = t0 < t1 ? t0 : t1; // _mm256_min_ps operand rule
                 if (tm < minDist) {
                     minDist = tm;
-                    minIdx = j;
+                    minIdx = h * 4 + k;
                 }
             }
         }
