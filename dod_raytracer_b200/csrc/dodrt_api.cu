@@ -360,6 +360,7 @@ int dodrt_scene_destroy(dodrt_scene *s)
 // Shared body of dodrt_scene_set_kdtree (prim_nums == nullptr: `tri_lanes` holds num_tri_lanes re-ordered lanes) and
 // dodrt_scene_set_kdtree_indexed (`tri_lanes` holds num_src_lanes lanes in creation order and lane i of the tree is
 // tri_lanes[prim_nums[i]]: Triangle::reorderLanesByIndices, triangle.cpp:349-367, done by the repack kernel's gather).
+static int ensureTris(dodrt_scene *s);
 static int setKdtree(dodrt_scene *s, const uint64_t *nodes, uint32_t num_nodes, const float *tri_lanes, uint32_t num_src_lanes,
                      const uint32_t *prim_nums, uint32_t num_tri_lanes, const float bounds[6])
 {
@@ -409,7 +410,6 @@ static int setKdtree(dodrt_scene *s, const uint64_t *nodes, uint32_t num_nodes, 
         if (e == cudaSuccess && prim_nums) {
             e = cudaMemcpy(d_prim, prim_nums, (size_t)num_tri_lanes * sizeof(uint32_t), cudaMemcpyHostToDevice);
         }
-        if (e == cudaSuccess) e = cudaMalloc(&s->d_tris, (size_t)num_tri_lanes * kLane * 3 * sizeof(float4));
         if (e == cudaSuccess) e = cudaMalloc(&s->d_lanes4, laneBytes);
         if (e == cudaSuccess) e = launch_repack_triangles(d_lanes, d_prim, num_tri_lanes, s->d_tris, s->d_lanes4, nullptr);
         if (e == cudaSuccess) e = cudaDeviceSynchronize();
@@ -419,7 +419,7 @@ static int setKdtree(dodrt_scene *s, const uint64_t *nodes, uint32_t num_nodes, 
         s->launches.fetch_add(1);
     }
     s->dev.nodes = s->d_nodes;
-    s->dev.tris = s->d_tris;
+    s->dev.tris = nullptr; // per-triangle records: built on demand by ensureTris (variants 0-2 only)
     s->dev.lanes4 = s->d_lanes4;
     s->dev.num_nodes = num_nodes;
     s->dev.num_tri_lanes = num_tri_lanes;
@@ -428,6 +428,7 @@ static int setKdtree(dodrt_scene *s, const uint64_t *nodes, uint32_t num_nodes, 
         s->dev.bmax[i] = bounds[3 + i];
     }
     s->treeDepth = depth;
+    if (s->variant >= 0 && s->variant < 3) return ensureTris(s); // DODRT_VARIANT / an earlier set_kernel_variant
     return DODRT_OK;
 }
 
@@ -634,12 +635,29 @@ int dodrt_scene_set_shading_indexed(dodrt_scene *s, const void *tri_attributes, 
                       plane_colors);
 }
 
+// Variants 0-2 read one 48-B record per triangle slot (133 MB for the 871k-triangle mesh, 2 GB for config 5); the
+// default kernels never do, so the array only exists once such a variant has been asked for.
+static int ensureTris(dodrt_scene *s)
+{
+    if (s->d_tris || s->dev.num_tri_lanes == 0) return DODRT_OK;
+    DeviceGuard guard(s->device);
+    if (!guard.ok) return fail(DODRT_E_CUDA, "cannot select device %d", s->device);
+    CUDA_TRY(cudaMalloc(&s->d_tris, (size_t)s->dev.num_tri_lanes * kLane * 3 * sizeof(float4)));
+    cudaError_t e = launch_tris_from_lanes4(s->d_lanes4, s->dev.num_tri_lanes, s->d_tris, nullptr);
+    if (e == cudaSuccess) e = cudaDeviceSynchronize();
+    if (e != cudaSuccess) return fail(DODRT_E_CUDA, "triangle records: %s", cudaGetErrorString(e));
+    s->dev.tris = s->d_tris;
+    s->launches.fetch_add(1);
+    return DODRT_OK;
+}
+
 int dodrt_scene_set_kernel_variant(dodrt_scene *s, int variant)
 {
     if (!s) return fail(DODRT_E_INVALID, "scene is NULL");
     if (variant >= kNumVariants) return fail(DODRT_E_INVALID, "kernel variant %d out of range [0,%d)", variant, kNumVariants);
     std::lock_guard<std::mutex> lock(s->mutex);
     s->variant = variant < 0 ? default_variant() : variant;
+    if (s->variant >= 0 && s->variant < 3) return ensureTris(s);
     return DODRT_OK;
 }
 

@@ -682,9 +682,11 @@ __global__ void repack_triangles_kernel(const float *__restrict__ lanes, const u
     const float Bx = lane[3 * kLane + j], By = lane[4 * kLane + j], Bz = lane[5 * kLane + j];
     const float Cx = lane[6 * kLane + j], Cy = lane[7 * kLane + j], Cz = lane[8 * kLane + j];
     // avxVec3Sub(B, A), avxVec3Sub(C, A): triangle.cpp:66-67
-    tris[idx * 3 + 0] = make_float4(Ax, Ay, Az, Bx - Ax);
-    tris[idx * 3 + 1] = make_float4(By - Ay, Bz - Az, Cx - Ax, Cy - Ay);
-    tris[idx * 3 + 2] = make_float4(Cz - Az, 0.0f, 0.0f, 0.0f);
+    if (tris) { // only the A/B variants 0-2 read the per-triangle records
+        tris[idx * 3 + 0] = make_float4(Ax, Ay, Az, Bx - Ax);
+        tris[idx * 3 + 1] = make_float4(By - Ay, Bz - Az, Cx - Ax, Cy - Ay);
+        tris[idx * 3 + 2] = make_float4(Cz - Az, 0.0f, 0.0f, 0.0f);
+    }
     float *out = lanes4 + (idx / kLane) * 72 + j; // SoA lane: A, AB, AC components, 8 slots each
     out[0 * kLane] = Ax;
     out[1 * kLane] = Ay;
@@ -695,6 +697,19 @@ __global__ void repack_triangles_kernel(const float *__restrict__ lanes, const u
     out[6 * kLane] = Cx - Ax;
     out[7 * kLane] = Cy - Ay;
     out[8 * kLane] = Cz - Az;
+}
+
+// The per-triangle records of variants 0-2 from the SoA lanes (A, AB, AC are already there): built on demand only.
+__global__ void tris_from_lanes4_kernel(const float *__restrict__ lanes4, uint32_t numLanes, float4 *__restrict__ tris)
+{
+    const uint64_t idx = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= (uint64_t)numLanes * kLane) {
+        return;
+    }
+    const float *l = lanes4 + (idx / kLane) * 72 + (idx % kLane);
+    tris[idx * 3 + 0] = make_float4(l[0 * kLane], l[1 * kLane], l[2 * kLane], l[3 * kLane]);
+    tris[idx * 3 + 1] = make_float4(l[4 * kLane], l[5 * kLane], l[6 * kLane], l[7 * kLane]);
+    tris[idx * 3 + 2] = make_float4(l[8 * kLane], 0.0f, 0.0f, 0.0f);
 }
 
 // out[lane][w] = in[primNums[lane]][w]: the lane re-order for any per-lane record of `wordsPerLane` 32-bit words
@@ -898,6 +913,16 @@ cudaError_t launch_gather_lanes(const uint32_t *d_in, const uint32_t *d_prim_num
     const int block = 256;
     gather_lanes_kernel<<<(unsigned)((n + block - 1) / block), block, 0, stream>>>(d_in, d_prim_nums, num_lanes, words_per_lane,
                                                                                     d_out);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_tris_from_lanes4(const float4 *d_lanes4, uint32_t num_lanes, float4 *d_tris, cudaStream_t stream)
+{
+    const uint64_t n = (uint64_t)num_lanes * kLane;
+    if (n == 0) return cudaSuccess;
+    const int block = 256;
+    tris_from_lanes4_kernel<<<(unsigned)((n + block - 1) / block), block, 0, stream>>>(reinterpret_cast<const float *>(d_lanes4),
+                                                                                        num_lanes, d_tris);
     return cudaGetLastError();
 }
 

@@ -99,6 +99,8 @@ cudaError_t launch_assemble(const dodrt_frame &frame, uint32_t tiles_x, const do
 // `d_prim_nums` (optional): output lane i = source lane d_prim_nums[i] (Triangle::reorderLanesByIndices fused in).
 cudaError_t launch_repack_triangles(const float *d_lanes, const uint32_t *d_prim_nums, uint32_t num_lanes, float4 *d_tris,
                                     float4 *d_lanes4, cudaStream_t stream);
+// per-triangle 48-B records (variants 0-2 only) from the SoA lanes; `d_tris` of launch_repack_triangles may be nullptr
+cudaError_t launch_tris_from_lanes4(const float4 *d_lanes4, uint32_t num_lanes, float4 *d_tris, cudaStream_t stream);
 // generic per-lane gather (shading attributes): out[i] = in[d_prim_nums[i]], `words_per_lane` 32-bit words each
 cudaError_t launch_gather_lanes(const uint32_t *d_in, const uint32_t *d_prim_nums, uint32_t num_lanes, uint32_t words_per_lane,
                                 uint32_t *d_out, cudaStream_t stream);
