@@ -100,6 +100,17 @@ struct dodrt_scene {
     // staging memory of the host-buffer entry points: a private pool that keeps freed blocks cached
     // (release threshold = max), so a per-frame call does not pay for physical allocation every time
     cudaMemPool_t pool = nullptr;
+    // Persistent donation queues of the donating kernel (variant 7): a small ring, each zero-filled once and then
+    // re-used with a fresh epoch per launch, so a pass costs neither an allocation nor a memset of the ready words.
+    // Launches on one stream share a queue (they cannot overlap); a queue moves to another stream only when the launch
+    // that used it has finished (its event); with more than kDonateQueues streams in flight a launch falls back to a
+    // per-launch pool allocation.
+    static constexpr int kDonateQueues = 4;
+    void *donateQueue[kDonateQueues] = {nullptr, nullptr, nullptr, nullptr};
+    cudaEvent_t donateDone[kDonateQueues] = {nullptr, nullptr, nullptr, nullptr};
+    bool donateBusy[kDonateQueues] = {false, false, false, false};
+    cudaStream_t donateOwner[kDonateQueues] = {nullptr, nullptr, nullptr, nullptr}; // stream of the launch that used it last
+    std::atomic<uint32_t> donateEpoch{0};
 };
 
 namespace {
@@ -209,6 +220,51 @@ int ensureStream(dodrt_scene *s)
     return DODRT_OK;
 }
 
+// launch_trace with the scene's donation machinery: a persistent queue when one is free, else the pool.
+cudaError_t launchTraceOn(dodrt_scene *s, TraceMode mode, const TraceParams &p, cudaStream_t stream)
+{
+    const LaunchConfig &cfg = s->cfg[p.variant][mode];
+    if (p.variant != kDonateVariant || s->dev.num_nodes == 0 || !(p.classes & DODRT_CLS_TREE)) {
+        return launch_trace(mode, p, cfg, stream, nullptr);
+    }
+    int slot = -1;
+    {
+        std::lock_guard<std::mutex> lock(s->mutex);
+        // launches on one stream run one after the other, so they can share a queue without waiting for anything
+        for (int q = 0; q < dodrt_scene::kDonateQueues && slot < 0; q++) {
+            if (s->donateQueue[q] && s->donateBusy[q] && s->donateOwner[q] == stream) slot = q;
+        }
+        for (int q = 0; q < dodrt_scene::kDonateQueues && slot < 0; q++) {
+            if (s->donateBusy[q] && cudaEventQuery(s->donateDone[q]) == cudaSuccess) s->donateBusy[q] = false;
+            if (s->donateBusy[q]) continue; // in flight on another stream
+            if (!s->donateQueue[q]) {
+                const size_t bytes = donation_queue_bytes(cfg);
+                if (cudaMalloc(&s->donateQueue[q], bytes) != cudaSuccess ||
+                    cudaMemset(s->donateQueue[q], 0, bytes) != cudaSuccess ||
+                    cudaEventCreateWithFlags(&s->donateDone[q], cudaEventDisableTiming) != cudaSuccess) {
+                    cudaGetLastError();
+                    if (s->donateQueue[q]) cudaFree(s->donateQueue[q]);
+                    s->donateQueue[q] = nullptr;
+                    break; // out of memory: fall back to the pool path below
+                }
+            }
+            slot = q;
+        }
+        if (slot >= 0) {
+            s->donateBusy[slot] = true;
+            s->donateOwner[slot] = stream;
+        }
+    }
+    if (slot < 0) {
+        return launch_trace(mode, p, cfg, stream, s->pool);
+    }
+    uint32_t epoch = s->donateEpoch.fetch_add(1) + 1u;
+    if (epoch == 0u) epoch = s->donateEpoch.fetch_add(1) + 1u; // 0 marks "never written"
+    cudaError_t e = launch_trace(mode, p, cfg, stream, nullptr, s->donateQueue[slot], epoch);
+    cudaEventRecord(s->donateDone[slot], stream);
+    return e;
+}
+
 // Traces local tiles [tileBegin, tileBegin + tileCount) of the frame (tileCount is clamped); d_hits / d_visible
 // always point at slot 0 of the call's result buffers.
 int launchFrame(dodrt_scene *s, TraceMode mode, const dodrt_frame *frame, const float *d_xs, const float *d_ys,
@@ -248,7 +304,9 @@ int launchFrame(dodrt_scene *s, TraceMode mode, const dodrt_frame *frame, const 
     p.num_local_tiles = tiles;
     p.tile_order = nullptr;
     static const bool orderTiles = [] { const char *e = std::getenv("DODRT_TILE_ORDER"); return !e || std::atoi(e) != 0; }();
-    if (orderTiles && (frame->classes & DODRT_CLS_TREE) && s->dev.num_nodes != 0 && tiles >= 64) {
+    // (not for the donating kernel: its tail is spread over the idle warps anyway -- measured 0.750 vs 0.760 ms per rank of
+    // 8 -- and the order kernel plus its allocation are ~10 us of a 0.25 ms pass)
+    if (orderTiles && p.variant != kDonateVariant && (frame->classes & DODRT_CLS_TREE) && s->dev.num_nodes != 0 && tiles >= 64) {
         int rc = ensurePool(s);
         if (rc != DODRT_OK) return rc;
         CUDA_TRY(cudaMallocFromPoolAsync(&p.tile_order, sizeof(uint32_t) * tiles, s->pool, stream));
@@ -257,7 +315,7 @@ int launchFrame(dodrt_scene *s, TraceMode mode, const dodrt_frame *frame, const 
         int rc = ensurePool(s);
         if (rc != DODRT_OK) return rc;
     }
-    cudaError_t le = launch_trace(mode, p, s->cfg[p.variant][mode], stream, s->pool);
+    cudaError_t le = launchTraceOn(s, mode, p, stream);
     if (p.tile_order) {
         cudaFreeAsync(p.tile_order, stream);
         s->launches.fetch_add(1);
@@ -337,6 +395,10 @@ int dodrt_scene_destroy(dodrt_scene *s)
     if (s->stream) cudaStreamDestroy(s->stream);
     if (s->copyStream) cudaStreamDestroy(s->copyStream);
     if (s->pool) cudaMemPoolDestroy(s->pool);
+    for (int q = 0; q < dodrt_scene::kDonateQueues; q++) {
+        if (s->donateDone[q]) cudaEventDestroy(s->donateDone[q]);
+        if (s->donateQueue[q]) cudaFree(s->donateQueue[q]);
+    }
     freeDevice(s->d_nodes);
     freeDevice(s->d_tris);
     freeDevice(s->d_lanes4);
@@ -693,7 +755,7 @@ int dodrt_intersect_device(dodrt_scene *s, const dodrt_ray *d_rays, uint64_t num
         int rc = ensurePool(s);
         if (rc != DODRT_OK) return rc;
     }
-    CUDA_TRY(launch_trace(kModeRays, p, s->cfg[p.variant][kModeRays], static_cast<cudaStream_t>(stream), s->pool));
+    CUDA_TRY(launchTraceOn(s, kModeRays, p, static_cast<cudaStream_t>(stream)));
     s->launches.fetch_add(1);
     return DODRT_OK;
 }
@@ -985,13 +1047,13 @@ int dodrt_render(dodrt_scene *s, const dodrt_frame *frame, const float *xs, cons
         // bounce passes: incoherent rays, long tails (dragon as-is frame 182 -> 166 ms with donation)
         p.variant = resolve_variant(s->variant, s->cfg[kDonateVariant][kModeRays], p.count, true, s->dev.num_nodes >= kBigTreeNodes);
         p.counter = nextCounter(s);
-        e = launch_trace(kModeRays, p, s->cfg[p.variant][kModeRays], st, s->pool); // closest-hit chain, main.cpp:314-321
+        e = launchTraceOn(s, kModeRays, p, st); // closest-hit chain, main.cpp:314-321
         if (e == cudaSuccess) s->launches.fetch_add(1);
         for (uint32_t l = 0; l < num_lights && e == cudaSuccess; l++) { // canSeeLight per light, main.cpp:226
             p.counter = nextCounter(s);
             p.visible = rp.visible + n * l;
             for (int c = 0; c < 3; c++) p.light[c] = rp.lights[l][c];
-            e = launch_trace(kModeShadowRays, p, s->cfg[p.variant][kModeShadowRays], st, s->pool);
+            e = launchTraceOn(s, kModeShadowRays, p, st);
             if (e == cudaSuccess) s->launches.fetch_add(1);
         }
         if (e == cudaSuccess) e = launch_render_shade(rp, k, st);

@@ -87,8 +87,8 @@ struct SuspendedRay {
 
 // `fin` lives in the caller's local memory (its address escapes to this non-inlined routine), so the finisher
 // record -- never read by the traversal itself -- does not occupy registers across the voted loop.
-__device__ __noinline__ void donate_store(uint32_t *slots, uint32_t *ready, uint32_t slot, const SuspendedRay &r,
-                                          const Finish *fin)
+__device__ __noinline__ void donate_store(uint32_t *slots, uint32_t *ready, uint32_t epoch, uint32_t slot,
+                                          const SuspendedRay &r, const Finish *fin)
 {
     float4 *w = reinterpret_cast<float4 *>(slots + (size_t)slot * kDonateSlotWords);
     w[0] = r.w[0];
@@ -104,7 +104,7 @@ __device__ __noinline__ void donate_store(uint32_t *slots, uint32_t *ready, uint
         stk[3 * i + 2] = __float_as_uint(r.stackTmax[i]);
     }
     __threadfence();
-    *reinterpret_cast<volatile uint32_t *>(ready + slot) = 1u;
+    *reinterpret_cast<volatile uint32_t *>(ready + slot) = epoch;
 }
 
 // Suspends up to `want` live rays of the warp into the queue (lanes in ascending order).  The lanes concerned have
@@ -142,7 +142,7 @@ __device__ __forceinline__ void donate_live_rays(const TraceParams &p, uint32_t 
         r.stackTmin = stackTmin;
         r.stackTmax = stackTmax;
         r.sp = st.sp;
-        donate_store(p.donate_slots, p.donate_ready, (uint32_t)base + rank, r, fin);
+        donate_store(p.donate_slots, p.donate_ready, p.donate_epoch, (uint32_t)base + rank, r, fin);
         st.live = false;
         donated = true;
     }
@@ -249,7 +249,7 @@ __device__ __forceinline__ void donate_helper_loop(const TraceParams &p)
         if (lane == 0) {
             unsigned ns = 200;
             for (;;) {
-                if (*reinterpret_cast<const volatile uint32_t *>(p.donate_ready + ticket) != 0u) {
+                if (*reinterpret_cast<const volatile uint32_t *>(p.donate_ready + ticket) == p.donate_epoch) {
                     ready = 1;
                     break;
                 }

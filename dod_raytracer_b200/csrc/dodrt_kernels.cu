@@ -842,29 +842,44 @@ cudaError_t trace_launch_config(int device, TraceMode mode, int variant, LaunchC
     }
 }
 
+size_t donation_queue_bytes(const LaunchConfig &cfg)
+{
+    // donors check `tail <= capacity / 2` before reserving; every warp of the grid can pass that check at the same
+    // time and reserve up to 32 slots, hence twice the grid's threads
+    const size_t cap = (size_t)cfg.grid * cfg.block * 2;
+    const size_t readyBytes = (cap * sizeof(uint32_t) + 255) & ~(size_t)255;
+    return readyBytes + cap * kDonateSlotWords * sizeof(uint32_t);
+}
+
 cudaError_t launch_trace(TraceMode mode, const TraceParams &params, const LaunchConfig &cfg, cudaStream_t stream,
-                         cudaMemPool_t pool)
+                         cudaMemPool_t pool, void *persistentQueue, uint32_t epoch)
 {
     TraceParams p = params;
     cudaError_t e = cudaMemsetAsync(p.counter, 0, sizeof(unsigned long long) * kCounterWords, stream);
     if (e != cudaSuccess) return e;
-    // variant 7: the donation queue lives for this launch only (stream-ordered allocation from the scene's pool);
-    // one slot per thread of the grid bounds the number of rays that can ever be suspended at once
+    // variant 7: the donation queue -- one slot per thread of the grid (x2) bounds the number of rays that can ever be
+    // suspended at once
     p.donate_slots = p.donate_ready = nullptr;
     p.donate_capacity = 0;
+    p.donate_epoch = 1;
     void *queue = nullptr;
     static const bool donateOn = [] { const char *e = std::getenv("DODRT_DONATE"); return !e || std::atoi(e) != 0; }();
-    if (donateOn && p.variant == kDonateVariant && pool != nullptr && p.scene.num_nodes != 0 && (p.classes & DODRT_CLS_TREE)) {
-        // donors check `tail <= capacity / 2` before reserving; every warp of the grid can pass that check at the same
-        // time and reserve up to 32 slots, hence twice the grid's threads
+    if (donateOn && p.variant == kDonateVariant && p.scene.num_nodes != 0 && (p.classes & DODRT_CLS_TREE) &&
+        (persistentQueue != nullptr || pool != nullptr)) {
         const size_t cap = (size_t)cfg.grid * cfg.block * 2;
         const size_t readyBytes = (cap * sizeof(uint32_t) + 255) & ~(size_t)255;
-        e = cudaMallocFromPoolAsync(&queue, readyBytes + cap * kDonateSlotWords * sizeof(uint32_t), pool, stream);
-        if (e != cudaSuccess) return e;
-        e = cudaMemsetAsync(queue, 0, readyBytes, stream);
-        if (e != cudaSuccess) return e;
-        p.donate_ready = static_cast<uint32_t *>(queue);
-        p.donate_slots = reinterpret_cast<uint32_t *>(static_cast<char *>(queue) + readyBytes);
+        void *mem = persistentQueue;
+        if (mem != nullptr && epoch != 0u) {
+            p.donate_epoch = epoch; // nothing to clear: words written by earlier launches carry other epochs
+        } else {
+            e = cudaMallocFromPoolAsync(&queue, readyBytes + cap * kDonateSlotWords * sizeof(uint32_t), pool, stream);
+            if (e != cudaSuccess) return e;
+            e = cudaMemsetAsync(queue, 0, readyBytes, stream);
+            if (e != cudaSuccess) return e;
+            mem = queue;
+        }
+        p.donate_ready = static_cast<uint32_t *>(mem);
+        p.donate_slots = reinterpret_cast<uint32_t *>(static_cast<char *>(mem) + readyBytes);
         p.donate_capacity = (uint32_t)cap;
     }
     if (p.tile_order && (mode == kModePrimary || mode == kModeShadow)) {

@@ -43,7 +43,8 @@ struct TraceParams {
     // variant 7 (ray donation, dodrt_donate.inl): per-launch queue of suspended rays, filled by warps that are still
     // working when others have run out of work; nullptr = donation off
     uint32_t *donate_slots;   // donate_capacity x kDonateSlotWords words
-    uint32_t *donate_ready;   // donate_capacity flags, zeroed before the launch
+    uint32_t *donate_ready;   // donate_capacity words; slot i is filled when donate_ready[i] == donate_epoch
+    uint32_t donate_epoch;    // non-zero, unique per launch on a persistent queue (stale words of earlier launches never match)
     uint32_t donate_capacity;
 };
 
@@ -67,9 +68,12 @@ struct LaunchConfig {
 cudaError_t trace_launch_config(int device, TraceMode mode, int variant, LaunchConfig *cfg);
 int resolve_variant(int variant, const LaunchConfig &donateCfg, uint64_t count, bool split, bool bigTree);
 constexpr uint32_t kBigTreeNodes = 8192;
-// `pool` (optional): stream-ordered pool the donation queue of variant 7 is taken from; nullptr = no donation
+// Donation queue of variant 7: either `queue` (persistent memory of donation_queue_bytes(cfg), zero-filled once when it was
+// allocated, used with a fresh non-zero `epoch` per launch -- nothing to clear), or a per-launch allocation from `pool`
+// (stream-ordered, ready words zeroed on the stream); neither = no donation.
+size_t donation_queue_bytes(const LaunchConfig &cfg);
 cudaError_t launch_trace(TraceMode mode, const TraceParams &p, const LaunchConfig &cfg, cudaStream_t stream,
-                         cudaMemPool_t pool = nullptr);
+                         cudaMemPool_t pool = nullptr, void *queue = nullptr, uint32_t epoch = 0);
 
 // ---- shading / bounce loop (dodrt_render_kernels.cu): rayTrace, main.cpp:273-347 ---------------------------------
 constexpr int kMaxLights = 16;
