@@ -316,6 +316,15 @@ int launchFrame(dodrt_scene *s, TraceMode mode, const dodrt_frame *frame, const 
         if (rc != DODRT_OK) return rc;
     }
     cudaError_t le = launchTraceOn(s, mode, p, stream);
+#ifdef DODRT_TIMELINE
+    { // debug build: where does a pass spend its time?  (start, first warp out of work, last warp busy, last helper gone)
+        unsigned long long tl[4];
+        cudaStreamSynchronize(stream);
+        cudaMemcpy(tl, p.counter + 24, 32, cudaMemcpyDeviceToHost);
+        std::fprintf(stderr, "timeline mode %d variant %d count %llu: first-idle %+.1f us, last-busy %+.1f us, end %+.1f us\n", (int)mode,
+                     p.variant, (unsigned long long)p.count, (tl[1] - tl[0]) * 1e-3, (tl[2] - tl[0]) * 1e-3, (tl[3] - tl[0]) * 1e-3);
+    }
+#endif
     if (p.tile_order) {
         cudaFreeAsync(p.tile_order, stream);
         s->launches.fetch_add(1);

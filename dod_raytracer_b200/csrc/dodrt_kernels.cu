@@ -561,6 +561,13 @@ __global__ void __launch_bounds__(128, VARIANT >= kDonateVariant ? 5 : DODRT_MIN
     if (VARIANT == kDonateVariant && p.donate_slots != nullptr && lane == 0) {
         atomicAdd(p.counter + kDonateStarted, 1ull); // see donate_helper_loop
     }
+#ifdef DODRT_TIMELINE
+    if (lane == 0) {
+        unsigned long long t;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+        atomicMin(p.counter + 24, t); // kernel start
+    }
+#endif
     for (;;) {
         unsigned long long base = 0;
         if (lane == 0) {
@@ -656,9 +663,24 @@ __global__ void __launch_bounds__(128, VARIANT >= kDonateVariant ? 5 : DODRT_MIN
             }
         }
     }
+#ifdef DODRT_TIMELINE
+    if (lane == 0) {
+        unsigned long long t;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+        atomicMin(p.counter + 25, t); // first warp out of work
+        atomicMax(p.counter + 26, t); // last warp out of its main loop
+    }
+#endif
 #ifndef DBG_NOHELPER
     if (VARIANT == kDonateVariant && p.donate_slots != nullptr) {
         donate_helper_loop(p);
+    }
+#endif
+#ifdef DODRT_TIMELINE
+    if (lane == 0) {
+        unsigned long long t;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+        atomicMax(p.counter + 27, t); // last helper gone
     }
 #endif
 }
@@ -857,6 +879,9 @@ cudaError_t launch_trace(TraceMode mode, const TraceParams &params, const Launch
     TraceParams p = params;
     cudaError_t e = cudaMemsetAsync(p.counter, 0, sizeof(unsigned long long) * kCounterWords, stream);
     if (e != cudaSuccess) return e;
+#ifdef DODRT_TIMELINE
+    cudaMemsetAsync(p.counter + 24, 0xFF, 16, stream); // the two minima
+#endif
     // variant 7: the donation queue -- one slot per thread of the grid (x2) bounds the number of rays that can ever be
     // suspended at once
     p.donate_slots = p.donate_ready = nullptr;
