@@ -6,7 +6,8 @@
 // Neither answer depends on the ORDER in which candidates are met, so any structure that (a) never skips a
 // sphere the reference's arithmetic could accept and (b) reduces with the (t, id) key is result-identical.
 // This file is such a structure: a binary BVH over the primitives' boxes, built on the host at upload
-// (median split on the longest axis, leaves of <= 8 primitives), traversed per ray with a CONSERVATIVE test.
+// (median split on the longest axis, leaves of <= 8 primitives), traversed per ray -- near child first -- with a
+// CONSERVATIVE test.
 //
 // Why the test is conservative.  For a sphere (C, r) and a ray (O, D) the reference computes, in fp32,
 // L = C-O, distSq = L.L, tca = L.D, d2 = distSq - tca*tca and requires d2 < r^2.  With e = 2^-24 every product /
@@ -72,6 +73,38 @@ __device__ __forceinline__ bool prim_bvh_may_touch(const float4 lo4, const float
     return !(t0 > t1); // NaN anywhere -> keep the node
 }
 
+// Same test, also handing back key = entry distance - pad: with a smaller limit L' the node would still pass iff
+// key <= L' (its slab exits do not change), which lets a stacked node be dropped without touching memory again.  The
+// re-association (t0 - pad <= L' instead of t0 <= L' + pad) moves the threshold by an ulp of a bound that is padded four
+// times over.
+__device__ __forceinline__ bool prim_bvh_may_touch_key(const float4 lo4, const float4 hi4, const float o[3], const float d[3],
+                                                       const float inv[3], float tLimit, float &key)
+{
+    const float lo[3] = {lo4.x, lo4.y, lo4.z}, hi[3] = {hi4.x, hi4.y, hi4.z};
+    float far = 0.0f;
+#pragma unroll
+    for (int k = 0; k < 3; k++) {
+        far += fmaxf(fabsf(lo[k] - o[k]), fabsf(hi[k] - o[k]));
+    }
+    const float pad = kPrimBvhPad * far;
+    float t0 = 0.0f, t1 = tLimit + pad;
+#pragma unroll
+    for (int k = 0; k < 3; k++) {
+        const float a = lo[k] - pad - o[k], b = hi[k] + pad - o[k];
+        if (d[k] == 0.0f || !(fabsf(inv[k]) < 3.0e38f)) {
+            if (a > 0.0f || b < 0.0f) {
+                return false;
+            }
+        } else {
+            const float ta = a * inv[k], tb = b * inv[k];
+            t0 = fmaxf(t0, fminf(ta, tb));
+            t1 = fminf(t1, fmaxf(ta, tb));
+        }
+    }
+    key = t0 - pad; // NaN key: never dropped later (the comparison below is false)
+    return !(t0 > t1);
+}
+
 // One sphere of Sphere::intersect_impl (sphere.cpp:62-106): is it a candidate, and at which distance?
 __device__ __forceinline__ bool sphere_candidate(float cx, float cy, float cz, float radSq, const float o[3],
                                                  const float d[3], float &tm)
@@ -108,15 +141,18 @@ __device__ __forceinline__ bool prim_bvh_query(const float4 *__restrict__ nodes,
                                                float clip, Hit &hit)
 {
     const float inv[3] = {1.0f / d[0], 1.0f / d[1], 1.0f / d[2]};
-    uint32_t stack[48];
+    // Near child first: both children of an interior node are tested when it is visited, the one the ray enters first is
+    // descended, the other is stacked with its pruning key and dropped unread if a closer candidate turned up meanwhile.
+    // The answer is the (t, id) minimum over the same candidate set whatever the order, so only the work changes.
+    uint32_t stackNode[48];
+    float stackKey[48];
     int sp = 0;
-    uint32_t node = 0;
     float best = clip;
     uint32_t bestId = DODRT_MISS;
+    float4 lo4 = __ldg(nodes), hi4 = __ldg(nodes + 1);
+    bool live = prim_bvh_may_touch(lo4, hi4, o, d, inv, best);
     for (;;) {
-        const float4 lo4 = __ldg(nodes + 2 * node), hi4 = __ldg(nodes + 2 * node + 1);
-        bool descend = false;
-        if (prim_bvh_may_touch(lo4, hi4, o, d, inv, best)) {
+        if (live) {
             const uint32_t a = __float_as_uint(lo4.w), b = __float_as_uint(hi4.w);
             if (b & kPrimBvhLeaf) {
                 const uint32_t n = b & ~kPrimBvhLeaf;
@@ -146,17 +182,48 @@ __device__ __forceinline__ bool prim_bvh_query(const float4 *__restrict__ nodes,
                         }
                     }
                 }
+                live = false;
+            } else if (any) {
+                // any-hit: the first candidate ends the query, so the right child is only looked at if it is ever popped
+                stackNode[sp] = b;
+                stackKey[sp] = __int_as_float(0x7fc00000); // NaN = "not tested yet"
+                ++sp;
+                lo4 = __ldg(nodes + 2 * a);
+                hi4 = __ldg(nodes + 2 * a + 1);
+                live = prim_bvh_may_touch(lo4, hi4, o, d, inv, best);
             } else {
-                stack[sp++] = b; // right child later
-                node = a;
-                descend = true;
+                const float4 llo = __ldg(nodes + 2 * a), lhi = __ldg(nodes + 2 * a + 1);
+                const float4 rlo = __ldg(nodes + 2 * b), rhi = __ldg(nodes + 2 * b + 1);
+                float keyL = 0.0f, keyR = 0.0f;
+                const bool touchL = prim_bvh_may_touch_key(llo, lhi, o, d, inv, best, keyL);
+                const bool touchR = prim_bvh_may_touch_key(rlo, rhi, o, d, inv, best, keyR);
+                const bool leftFirst = !touchR || (touchL && !(keyR < keyL));
+                if (touchL && touchR) {
+                    stackNode[sp] = leftFirst ? b : a;
+                    stackKey[sp] = leftFirst ? keyR : keyL;
+                    ++sp;
+                }
+                live = touchL || touchR;
+                lo4 = leftFirst ? llo : rlo;
+                hi4 = leftFirst ? lhi : rhi;
             }
         }
-        if (!descend) {
-            if (sp == 0) {
+        if (!live) {
+            bool got = false;
+            while (sp > 0 && !got) {
+                --sp;
+                const float key = stackKey[sp];
+                if (!(key > best)) { // still within reach of the best candidate so far (or not tested yet)
+                    const uint32_t node = stackNode[sp];
+                    lo4 = __ldg(nodes + 2 * node);
+                    hi4 = __ldg(nodes + 2 * node + 1);
+                    got = key == key || prim_bvh_may_touch(lo4, hi4, o, d, inv, best);
+                }
+            }
+            if (!got) {
                 break;
             }
-            node = stack[--sp];
+            live = true;
         }
     }
     if (bestId == DODRT_MISS) {
