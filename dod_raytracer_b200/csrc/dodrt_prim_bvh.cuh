@@ -183,14 +183,6 @@ __device__ __forceinline__ bool prim_bvh_query(const float4 *__restrict__ nodes,
                     }
                 }
                 live = false;
-            } else if (any) {
-                // any-hit: the first candidate ends the query, so the right child is only looked at if it is ever popped
-                stackNode[sp] = b;
-                stackKey[sp] = __int_as_float(0x7fc00000); // NaN = "not tested yet"
-                ++sp;
-                lo4 = __ldg(nodes + 2 * a);
-                hi4 = __ldg(nodes + 2 * a + 1);
-                live = prim_bvh_may_touch(lo4, hi4, o, d, inv, best);
             } else {
                 const float4 llo = __ldg(nodes + 2 * a), lhi = __ldg(nodes + 2 * a + 1);
                 const float4 rlo = __ldg(nodes + 2 * b), rhi = __ldg(nodes + 2 * b + 1);
@@ -212,12 +204,11 @@ __device__ __forceinline__ bool prim_bvh_query(const float4 *__restrict__ nodes,
             bool got = false;
             while (sp > 0 && !got) {
                 --sp;
-                const float key = stackKey[sp];
-                if (!(key > best)) { // still within reach of the best candidate so far (or not tested yet)
+                if (!(stackKey[sp] > best)) { // still within reach of the best candidate so far
                     const uint32_t node = stackNode[sp];
                     lo4 = __ldg(nodes + 2 * node);
                     hi4 = __ldg(nodes + 2 * node + 1);
-                    got = key == key || prim_bvh_may_touch(lo4, hi4, o, d, inv, best);
+                    got = true;
                 }
             }
             if (!got) {
