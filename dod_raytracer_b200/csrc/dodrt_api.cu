@@ -238,7 +238,8 @@ cudaError_t launchTraceOn(dodrt_scene *s, TraceMode mode, const TraceParams &p, 
             if (s->donateBusy[q] && cudaEventQuery(s->donateDone[q]) == cudaSuccess) s->donateBusy[q] = false;
             if (s->donateBusy[q]) continue; // in flight on another stream
             if (!s->donateQueue[q]) {
-                const size_t bytes = donation_queue_bytes(cfg);
+                size_t bytes = 0; // a queue serves every mode: size it for the largest grid of the donating kernels
+                for (int m = 0; m < kNumModes; m++) bytes = std::max(bytes, donation_queue_bytes(s->cfg[kDonateVariant][m]));
                 if (cudaMalloc(&s->donateQueue[q], bytes) != cudaSuccess ||
                     cudaMemset(s->donateQueue[q], 0, bytes) != cudaSuccess ||
                     cudaEventCreateWithFlags(&s->donateDone[q], cudaEventDisableTiming) != cudaSuccess) {
