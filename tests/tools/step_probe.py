@@ -1,6 +1,9 @@
+#!/usr/bin/env python
+"""Per-step device times of back-to-back (or synchronised) primary passes of one workload: shows one-off allocation
+spikes and launch gaps that an average hides.   python tests/tools/step_probe.py [workload] [sync]"""
 import sys, os
 import numpy as np, torch
-sys.path.insert(0, "/root/repo")
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 from dod_raytracer_b200 import capi, host, workloads
 w = workloads.WORKLOADS[sys.argv[1] if len(sys.argv) > 1 else "dragon1080_primary"]
 sync_each = len(sys.argv) > 2 and sys.argv[2] == "sync"
