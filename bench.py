@@ -236,7 +236,10 @@ def main():
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
 
-    scene = hs.upload(local_rank)
+    t_up = time.perf_counter()
+    scene = hs.upload(local_rank)  # lanes in creation order + m_primNums: the GPU does the lane re-order (f-4)
+    torch.cuda.synchronize()
+    upload_s = time.perf_counter() - t_up
     sizes = hs.sizes()
     tile = tuple(int(x) for x in args.tile.split("x"))
     frame = distributed.rank_frame(w.width, w.height, w.classes, rank, world, tile)
@@ -465,7 +468,7 @@ def main():
                                       + ("; hit-record gather to rank 0 (NCCL) overlapped with the shadow pass, "
                                          "frame re-assembled by dodrt_frame_assemble_device" if world > 1 else ""),
                        "l2": "flushed between steps (512 MiB memset outside the per-step event bracket)",
-                       "host_build_s": round(build_s, 2), "wall_s_timed_region": round(wall, 3)},
+                       "host_build_s": round(build_s, 2), "upload_s": round(upload_s, 2), "wall_s_timed_region": round(wall, 3)},
             "e2e": e2e, "gpu_launches": launches, "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu_baseline,
             "parity": parity, "frame_ms": ms_per_step, "reference_frame": reference_frame}
     print(json.dumps(line), flush=True)
