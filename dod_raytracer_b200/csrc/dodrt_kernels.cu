@@ -551,8 +551,13 @@ template <int MODE> __global__ void order_tiles_kernel(const TraceParams p)
     }
 }
 
+// Resident blocks per SM the register allocation aims at.  The plain kernels fit 5 blocks (93-96 registers) on their
+// own; capped to 6 blocks (80 registers, 32-112 B of spills outside the leaf loop) the shadow pass is 4 % faster
+// (dragon4k 4415 -> 4550 Mrays/s), at 7 / 8 blocks the spills win (4184 / 3529).  Measured with NVVM's
+// rematerialisation off (see the Makefile); with it on, the cap made things worse.  The donating kernel stays at 5:
+// at 6 it is 2 % faster on a whole frame but slower on the short passes it exists for (0.754 vs 0.735 ms per rank of 8).
 #ifndef DODRT_MINBLOCKS
-#define DODRT_MINBLOCKS 1
+#define DODRT_MINBLOCKS 6
 #endif
 template <int MODE, int VARIANT>
 __global__ void __launch_bounds__(128, VARIANT >= kDonateVariant ? 5 : DODRT_MINBLOCKS) trace_kernel(const TraceParams p)
