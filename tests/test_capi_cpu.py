@@ -78,3 +78,14 @@ def test_no_gpu_means_loud_failure_not_fallback():
     with pytest.raises(capi.DodrtError) as e:
         capi.Scene(0)
     assert e.value.code == -2  # DODRT_E_CUDA
+
+
+def test_host_library_exports_every_declared_symbol():
+    """include/dodrt_host.h vs libdodrt_host.so (the host side above the C ABI)"""
+    from dod_raytracer_b200 import host
+    text = open(os.path.join(ROOT, "include", "dodrt_host.h")).read()
+    names = sorted(set(re.findall(r"DODRT_API\s+[\w\s\*]+?\b(dodrt_host_\w+)\s*\(", text)))
+    assert len(names) >= 30 and "dodrt_host_build_tree_ex" in names
+    lib = host.load()
+    for n in names:
+        assert getattr(lib, n) is not None, n
