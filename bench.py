@@ -145,15 +145,7 @@ class CpuPath:
             self.kind = "port"
             oracle_api.ensure_oracle_built()
             self.orc = oracle_api.Oracle()
-            a = host_arrays_fn()
-            s = oracle_api.Scene.__new__(oracle_api.Scene)
-            s.nodes, s.tri_lanes, s.bounds = a["nodes"], a["tri_lanes"], a["bounds"]
-            s.sphere_lanes, s.plane_lanes, s.box_lanes = a["sphere_lanes"], a["plane_lanes"], a["box_lanes"]
-            s.spheres = np.zeros((a["num_spheres"], 4), np.float32)
-            s.planes = np.zeros((a["num_planes"], 6), np.float32)
-            s.boxes = np.zeros((a["num_boxes"], 6), np.float32)
-            s.cylinders, s.epsilon = a["cylinders"], a["epsilon"]
-            self.scene = s
+            self.scene = oracle_api.Scene.from_host_arrays(host_arrays_fn())
 
     def frame(self):
         """one full frame on all host cores: returns (seconds, rays, t [n] float32, visible [n] uint8)"""

@@ -45,6 +45,22 @@ int fail(int code, const char *fmt, ...)
         }                                                                                                    \
     } while (0)
 
+// The ABI promises "never throws": every extern "C" body is a function-try-block that ends in DODRT_CATCH.
+int failException()
+{
+    try {
+        throw;
+    } catch (const std::bad_alloc &) {
+        return fail(DODRT_E_NOMEM, "out of host memory");
+    } catch (const std::exception &e) {
+        return fail(DODRT_E_INVALID, "unexpected C++ exception: %s", e.what());
+    } catch (...) {
+        return fail(DODRT_E_INVALID, "unexpected C++ exception");
+    }
+}
+#define DODRT_CATCH                                                                                           \
+    catch (...) { return failException(); }
+
 constexpr int kCounterSlots = 256;
 
 struct DeviceGuard {
@@ -157,12 +173,16 @@ int validateTree(const uint64_t *nodes, uint32_t numNodes, uint32_t numLanes, ui
     return DODRT_OK;
 }
 
+constexpr uint32_t kMaxTileSide = 4096; // keeps tile_w * tile_h and (width + tile_w - 1) inside 32 bits
 int checkFrame(const dodrt_frame *f)
 {
     if (!f) return fail(DODRT_E_INVALID, "frame is NULL");
     if (f->width == 0 || f->height == 0) return fail(DODRT_E_INVALID, "empty frame %ux%u", f->width, f->height);
     if (f->tile_w == 0 || f->tile_h == 0 || (f->tile_w % 8) || (f->tile_h % 4)) {
         return fail(DODRT_E_INVALID, "tile %ux%u must be a non-zero multiple of 8x4", f->tile_w, f->tile_h);
+    }
+    if (f->tile_w > kMaxTileSide || f->tile_h > kMaxTileSide) {
+        return fail(DODRT_E_INVALID, "tile %ux%u exceeds the limit of %u per side", f->tile_w, f->tile_h, kMaxTileSide);
     }
     if (f->tile_stride == 0) return fail(DODRT_E_INVALID, "tile_stride must be >= 1");
     if ((uint64_t)f->width * f->height >= 0xFFFFFFFFull) return fail(DODRT_E_INVALID, "frame too large");
@@ -171,8 +191,8 @@ int checkFrame(const dodrt_frame *f)
 
 void frameTiles(const dodrt_frame *f, uint32_t *tilesX, uint32_t *localTiles)
 {
-    const uint32_t tx = (f->width + f->tile_w - 1) / f->tile_w;
-    const uint32_t ty = (f->height + f->tile_h - 1) / f->tile_h;
+    const uint32_t tx = (uint32_t)(((uint64_t)f->width + f->tile_w - 1) / f->tile_w);
+    const uint32_t ty = (uint32_t)(((uint64_t)f->height + f->tile_h - 1) / f->tile_h);
     const uint64_t total = (uint64_t)tx * ty;
     *tilesX = tx;
     *localTiles = f->first_tile < total ? (uint32_t)((total - f->first_tile + f->tile_stride - 1) / f->tile_stride) : 0;
@@ -194,6 +214,8 @@ int ensurePool(dodrt_scene *s)
 {
     std::lock_guard<std::mutex> lock(s->mutex);
     if (!s->pool) {
+        DeviceGuard guard(s->device);
+        if (!guard.ok) return fail(DODRT_E_CUDA, "cannot select device %d", s->device);
         cudaMemPoolProps props{};
         props.allocType = cudaMemAllocationTypePinned;
         props.handleTypes = cudaMemHandleTypeNone;
@@ -211,6 +233,9 @@ int ensureStream(dodrt_scene *s)
     int rc = ensurePool(s);
     if (rc != DODRT_OK) return rc;
     std::lock_guard<std::mutex> lock(s->mutex);
+    // the streams must belong to the scene's device, whatever the calling thread's current device is
+    DeviceGuard guard(s->device);
+    if (!guard.ok) return fail(DODRT_E_CUDA, "cannot select device %d", s->device);
     if (!s->stream) {
         CUDA_TRY(cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking));
     }
@@ -221,49 +246,51 @@ int ensureStream(dodrt_scene *s)
 }
 
 // launch_trace with the scene's donation machinery: a persistent queue when one is free, else the pool.
+// The scene mutex is held from the choice of a queue until the launch has been enqueued AND its completion event
+// recorded: donateDone[q] therefore always describes the LAST launch that used queue q, and another host thread can
+// never see "busy" together with an event that is unrecorded or still holds an older, finished record (which would
+// hand one queue to two concurrent launches).  Launches are asynchronous, so the lock is held for microseconds.
 cudaError_t launchTraceOn(dodrt_scene *s, TraceMode mode, const TraceParams &p, cudaStream_t stream)
 {
     const LaunchConfig &cfg = s->cfg[p.variant][mode];
     if (p.variant != kDonateVariant || s->dev.num_nodes == 0 || !(p.classes & DODRT_CLS_TREE)) {
         return launch_trace(mode, p, cfg, stream, nullptr);
     }
+    std::unique_lock<std::mutex> lock(s->mutex);
     int slot = -1;
-    {
-        std::lock_guard<std::mutex> lock(s->mutex);
-        // launches on one stream run one after the other, so they can share a queue without waiting for anything
-        for (int q = 0; q < dodrt_scene::kDonateQueues && slot < 0; q++) {
-            if (s->donateQueue[q] && s->donateBusy[q] && s->donateOwner[q] == stream) slot = q;
-        }
-        for (int q = 0; q < dodrt_scene::kDonateQueues && slot < 0; q++) {
-            if (s->donateBusy[q] && cudaEventQuery(s->donateDone[q]) == cudaSuccess) s->donateBusy[q] = false;
-            if (s->donateBusy[q]) continue; // in flight on another stream
-            if (!s->donateQueue[q]) {
-                size_t bytes = 0; // a queue serves every mode: size it for the largest grid of the donating kernels
-                for (int m = 0; m < kNumModes; m++) bytes = std::max(bytes, donation_queue_bytes(s->cfg[kDonateVariant][m]));
-                if (cudaMalloc(&s->donateQueue[q], bytes) != cudaSuccess ||
-                    cudaMemset(s->donateQueue[q], 0, bytes) != cudaSuccess ||
-                    cudaEventCreateWithFlags(&s->donateDone[q], cudaEventDisableTiming) != cudaSuccess) {
-                    cudaGetLastError();
-                    if (s->donateQueue[q]) cudaFree(s->donateQueue[q]);
-                    s->donateQueue[q] = nullptr;
-                    break; // out of memory: fall back to the pool path below
-                }
+    // launches on one stream run one after the other, so they can share a queue without waiting for anything
+    for (int q = 0; q < dodrt_scene::kDonateQueues && slot < 0; q++) {
+        if (s->donateQueue[q] && s->donateBusy[q] && s->donateOwner[q] == stream) slot = q;
+    }
+    for (int q = 0; q < dodrt_scene::kDonateQueues && slot < 0; q++) {
+        if (s->donateBusy[q] && cudaEventQuery(s->donateDone[q]) == cudaSuccess) s->donateBusy[q] = false;
+        if (s->donateBusy[q]) continue; // in flight on another stream
+        if (!s->donateQueue[q]) {
+            size_t bytes = 0; // a queue serves every mode: size it for the largest grid of the donating kernels
+            for (int m = 0; m < kNumModes; m++) bytes = std::max(bytes, donation_queue_bytes(s->cfg[kDonateVariant][m]));
+            if (cudaMalloc(&s->donateQueue[q], bytes) != cudaSuccess ||
+                cudaMemset(s->donateQueue[q], 0, bytes) != cudaSuccess ||
+                cudaEventCreateWithFlags(&s->donateDone[q], cudaEventDisableTiming) != cudaSuccess) {
+                cudaGetLastError();
+                if (s->donateQueue[q]) cudaFree(s->donateQueue[q]);
+                s->donateQueue[q] = nullptr;
+                break; // out of memory: fall back to the pool path below
             }
-            slot = q;
         }
-        if (slot >= 0) {
-            s->donateBusy[slot] = true;
-            s->donateOwner[slot] = stream;
-        }
+        slot = q;
     }
     if (slot < 0) {
+        lock.unlock();
         return launch_trace(mode, p, cfg, stream, s->pool);
     }
     uint32_t epoch = s->donateEpoch.fetch_add(1) + 1u;
     if (epoch == 0u) epoch = s->donateEpoch.fetch_add(1) + 1u; // 0 marks "never written"
     cudaError_t e = launch_trace(mode, p, cfg, stream, nullptr, s->donateQueue[slot], epoch);
-    cudaEventRecord(s->donateDone[slot], stream);
-    return e;
+    const cudaError_t er = cudaEventRecord(s->donateDone[slot], stream);
+    // busy only with a recorded event behind it; if the record failed nobody may wait on the stale event
+    s->donateBusy[slot] = er == cudaSuccess;
+    s->donateOwner[slot] = stream;
+    return e != cudaSuccess ? e : er;
 }
 
 // Traces local tiles [tileBegin, tileBegin + tileCount) of the frame (tileCount is clamped); d_hits / d_visible
@@ -344,15 +371,16 @@ int dodrt_abi_version(void) { return DODRT_ABI_VERSION; }
 const char *dodrt_last_error(void) { return g_lastError.c_str(); }
 
 int dodrt_device_count(int *count)
-{
+try {
     if (!count) return fail(DODRT_E_INVALID, "count is NULL");
     *count = 0;
     CUDA_TRY(cudaGetDeviceCount(count));
     return DODRT_OK;
 }
+DODRT_CATCH
 
 int dodrt_scene_create(int device, dodrt_scene **scene)
-{
+try {
     if (!scene) return fail(DODRT_E_INVALID, "scene is NULL");
     *scene = nullptr;
     int count = 0;
@@ -396,9 +424,10 @@ int dodrt_scene_create(int device, dodrt_scene **scene)
     *scene = s;
     return DODRT_OK;
 }
+DODRT_CATCH
 
 int dodrt_scene_destroy(dodrt_scene *s)
-{
+try {
     if (!s) return DODRT_OK;
     DeviceGuard guard(s->device);
     cudaDeviceSynchronize();
@@ -428,6 +457,7 @@ int dodrt_scene_destroy(dodrt_scene *s)
     delete s;
     return DODRT_OK;
 }
+DODRT_CATCH
 
 // Shared body of dodrt_scene_set_kdtree (prim_nums == nullptr: `tri_lanes` holds num_tri_lanes re-ordered lanes) and
 // dodrt_scene_set_kdtree_indexed (`tri_lanes` holds num_src_lanes lanes in creation order and lane i of the tree is
@@ -506,17 +536,19 @@ static int setKdtree(dodrt_scene *s, const uint64_t *nodes, uint32_t num_nodes, 
 
 int dodrt_scene_set_kdtree(dodrt_scene *s, const uint64_t *nodes, uint32_t num_nodes, const float *tri_lanes,
                            uint32_t num_tri_lanes, const float bounds[6])
-{
+try {
     return setKdtree(s, nodes, num_nodes, tri_lanes, num_tri_lanes, nullptr, num_tri_lanes, bounds);
 }
+DODRT_CATCH
 
 int dodrt_scene_set_kdtree_indexed(dodrt_scene *s, const uint64_t *nodes, uint32_t num_nodes, const float *tri_lanes,
                                    uint32_t num_src_lanes, const uint32_t *prim_nums, uint32_t num_tri_lanes,
                                    const float bounds[6])
-{
+try {
     if (num_tri_lanes && !prim_nums) return fail(DODRT_E_INVALID, "prim_nums is NULL");
     return setKdtree(s, nodes, num_nodes, tri_lanes, num_src_lanes, prim_nums, num_tri_lanes, bounds);
 }
+DODRT_CATCH
 
 static int uploadLanes(dodrt_scene *s, float **slot, const float **view, uint32_t *countField, const float *lanes,
                        uint32_t count, uint32_t floatsPerLane)
@@ -552,6 +584,9 @@ static int uploadPrimBvh(dodrt_scene *s, const std::vector<float> &boxes, uint32
     *idsView = nullptr;
     static const bool enabled = [] { const char *e = std::getenv("DODRT_PRIM_BVH"); return !e || std::atoi(e) != 0; }();
     if (!enabled || count < kPrimBvhMinCount) return DODRT_OK;
+    for (float v : boxes) { // NaN / inf primitives cannot be boxed (and would break nth_element's ordering): brute force then
+        if (!std::isfinite(v)) return DODRT_OK;
+    }
     std::vector<PrimBvhNode> nodes;
     std::vector<uint32_t> ids;
     build_prim_bvh(boxes.data(), count, nodes, ids);
@@ -565,7 +600,7 @@ static int uploadPrimBvh(dodrt_scene *s, const std::vector<float> &boxes, uint32
 }
 
 int dodrt_scene_set_spheres(dodrt_scene *s, const float *sphere_lanes, uint32_t num_spheres)
-{
+try {
     if (!s) return fail(DODRT_E_INVALID, "scene is NULL");
     int rc = uploadLanes(s, &s->d_spheres, &s->dev.sphere_lanes, &s->dev.num_spheres, sphere_lanes, num_spheres, 4 * kLane);
     if (rc != DODRT_OK) return rc;
@@ -581,15 +616,17 @@ int dodrt_scene_set_spheres(dodrt_scene *s, const float *sphere_lanes, uint32_t 
     }
     return uploadPrimBvh(s, boxes, num_spheres, &s->d_sphereBvh, &s->d_sphereBvhIds, &s->dev.sphere_bvh, &s->dev.sphere_bvh_ids);
 }
+DODRT_CATCH
 
 int dodrt_scene_set_planes(dodrt_scene *s, const float *plane_lanes, uint32_t num_planes)
-{
+try {
     if (!s) return fail(DODRT_E_INVALID, "scene is NULL");
     return uploadLanes(s, &s->d_planes, &s->dev.plane_lanes, &s->dev.num_planes, plane_lanes, num_planes, 6 * kLane);
 }
+DODRT_CATCH
 
 int dodrt_scene_set_boxes(dodrt_scene *s, const float *box_lanes, uint32_t num_boxes)
-{
+try {
     if (!s) return fail(DODRT_E_INVALID, "scene is NULL");
     int rc = uploadLanes(s, &s->d_boxes, &s->dev.box_lanes, &s->dev.num_boxes, box_lanes, num_boxes, 6 * kLane);
     if (rc != DODRT_OK) return rc;
@@ -605,9 +642,10 @@ int dodrt_scene_set_boxes(dodrt_scene *s, const float *box_lanes, uint32_t num_b
     }
     return uploadPrimBvh(s, boxes, num_boxes, &s->d_boxBvh, &s->d_boxBvhIds, &s->dev.box_bvh, &s->dev.box_bvh_ids);
 }
+DODRT_CATCH
 
 int dodrt_scene_set_cylinders(dodrt_scene *s, const dodrt_cylinder *cylinders, uint32_t num_cylinders)
-{
+try {
     if (!s) return fail(DODRT_E_INVALID, "scene is NULL");
     if (num_cylinders && !cylinders) return fail(DODRT_E_INVALID, "NULL cylinders with non-zero count");
     std::lock_guard<std::mutex> lock(s->mutex);
@@ -624,6 +662,7 @@ int dodrt_scene_set_cylinders(dodrt_scene *s, const dodrt_cylinder *cylinders, u
     s->dev.num_cylinders = num_cylinders;
     return DODRT_OK;
 }
+DODRT_CATCH
 
 static int setShading(dodrt_scene *s, const void *tri_attributes, uint32_t num_src_lanes, const uint32_t *prim_nums,
                       uint32_t num_tri_lanes, const float *mesh_colors, uint32_t num_meshes, const float *sphere_colors,
@@ -693,19 +732,21 @@ static int setShading(dodrt_scene *s, const void *tri_attributes, uint32_t num_s
 
 int dodrt_scene_set_shading(dodrt_scene *s, const void *tri_attributes, uint32_t num_tri_lanes, const float *mesh_colors,
                             uint32_t num_meshes, const float *sphere_colors, const float *plane_colors)
-{
+try {
     return setShading(s, tri_attributes, num_tri_lanes, nullptr, num_tri_lanes, mesh_colors, num_meshes, sphere_colors,
                       plane_colors);
 }
+DODRT_CATCH
 
 int dodrt_scene_set_shading_indexed(dodrt_scene *s, const void *tri_attributes, uint32_t num_src_lanes,
                                     const uint32_t *prim_nums, uint32_t num_tri_lanes, const float *mesh_colors,
                                     uint32_t num_meshes, const float *sphere_colors, const float *plane_colors)
-{
+try {
     if (num_tri_lanes && !prim_nums) return fail(DODRT_E_INVALID, "prim_nums is NULL");
     return setShading(s, tri_attributes, num_src_lanes, prim_nums, num_tri_lanes, mesh_colors, num_meshes, sphere_colors,
                       plane_colors);
 }
+DODRT_CATCH
 
 // Variants 0-2 read one 48-B record per triangle slot (133 MB for the 871k-triangle mesh, 2 GB for config 5); the
 // default kernels never do, so the array only exists once such a variant has been asked for.
@@ -724,7 +765,7 @@ static int ensureTris(dodrt_scene *s)
 }
 
 int dodrt_scene_set_kernel_variant(dodrt_scene *s, int variant)
-{
+try {
     if (!s) return fail(DODRT_E_INVALID, "scene is NULL");
     if (variant >= kNumVariants) return fail(DODRT_E_INVALID, "kernel variant %d out of range [0,%d)", variant, kNumVariants);
     std::lock_guard<std::mutex> lock(s->mutex);
@@ -732,20 +773,22 @@ int dodrt_scene_set_kernel_variant(dodrt_scene *s, int variant)
     if (s->variant >= 0 && s->variant < 3) return ensureTris(s);
     return DODRT_OK;
 }
+DODRT_CATCH
 
 int dodrt_scene_set_epsilon(dodrt_scene *s, float epsilon)
-{
+try {
     if (!s) return fail(DODRT_E_INVALID, "scene is NULL");
     std::lock_guard<std::mutex> lock(s->mutex);
     s->dev.epsilon = epsilon;
     return DODRT_OK;
 }
+DODRT_CATCH
 
 // ---- device-resident entry points ---------------------------------------------------------------
 
 int dodrt_intersect_device(dodrt_scene *s, const dodrt_ray *d_rays, uint64_t num_rays, uint32_t classes,
                            dodrt_hit *d_hits, void *stream)
-{
+try {
     if (!s) return fail(DODRT_E_INVALID, "scene is NULL");
     if (num_rays == 0) return DODRT_OK;
     if (!d_rays || !d_hits) return fail(DODRT_E_INVALID, "NULL ray/hit buffer");
@@ -769,10 +812,11 @@ int dodrt_intersect_device(dodrt_scene *s, const dodrt_ray *d_rays, uint64_t num
     s->launches.fetch_add(1);
     return DODRT_OK;
 }
+DODRT_CATCH
 
 int dodrt_trace_primary_device(dodrt_scene *s, const dodrt_frame *frame, const float *d_xs, const float *d_ys,
                                dodrt_hit *d_hits, void *stream)
-{
+try {
     if (!s) return fail(DODRT_E_INVALID, "scene is NULL");
     int rc = checkFrame(frame);
     if (rc != DODRT_OK) return rc;
@@ -781,10 +825,11 @@ int dodrt_trace_primary_device(dodrt_scene *s, const dodrt_frame *frame, const f
     if (!guard.ok) return fail(DODRT_E_CUDA, "cannot select device %d", s->device);
     return launchFrame(s, kModePrimary, frame, d_xs, d_ys, d_hits, nullptr, nullptr, static_cast<cudaStream_t>(stream));
 }
+DODRT_CATCH
 
 int dodrt_trace_shadow_device(dodrt_scene *s, const dodrt_frame *frame, const float *d_xs, const float *d_ys,
                               const dodrt_hit *d_hits, const float light[3], uint8_t *d_visible, void *stream)
-{
+try {
     if (!s) return fail(DODRT_E_INVALID, "scene is NULL");
     int rc = checkFrame(frame);
     if (rc != DODRT_OK) return rc;
@@ -794,11 +839,12 @@ int dodrt_trace_shadow_device(dodrt_scene *s, const dodrt_frame *frame, const fl
     return launchFrame(s, kModeShadow, frame, d_xs, d_ys, const_cast<dodrt_hit *>(d_hits), light, d_visible,
                        static_cast<cudaStream_t>(stream));
 }
+DODRT_CATCH
 
 int dodrt_frame_assemble_device(dodrt_scene *s, const dodrt_frame *frame, const dodrt_hit *d_compact_hits,
                                 const uint8_t *d_compact_visible, uint64_t slots_per_rank, dodrt_hit *d_hits_out,
                                 uint8_t *d_visible_out, void *stream)
-{
+try {
     if (!s) return fail(DODRT_E_INVALID, "scene is NULL");
     int rc = checkFrame(frame);
     if (rc != DODRT_OK) return rc;
@@ -821,11 +867,12 @@ int dodrt_frame_assemble_device(dodrt_scene *s, const dodrt_frame *frame, const 
     s->launches.fetch_add(1);
     return DODRT_OK;
 }
+DODRT_CATCH
 
 // ---- host-buffer entry points -------------------------------------------------------------------
 
 int dodrt_intersect(dodrt_scene *s, const dodrt_ray *rays, uint64_t num_rays, uint32_t classes, dodrt_hit *hits)
-{
+try {
     if (!s) return fail(DODRT_E_INVALID, "scene is NULL");
     if (num_rays == 0) return DODRT_OK;
     if (!rays || !hits) return fail(DODRT_E_INVALID, "NULL ray/hit buffer");
@@ -853,10 +900,11 @@ int dodrt_intersect(dodrt_scene *s, const dodrt_ray *rays, uint64_t num_rays, ui
     if (e != cudaSuccess) return fail(DODRT_E_CUDA, "dodrt_intersect: %s", cudaGetErrorString(e));
     return DODRT_OK;
 }
+DODRT_CATCH
 
 int dodrt_trace_frame(dodrt_scene *s, const dodrt_frame *frame, const float *xs, const float *ys, const float *lights,
                       uint32_t num_lights, dodrt_hit *hits, uint8_t *visible)
-{
+try {
     if (!s) return fail(DODRT_E_INVALID, "scene is NULL");
     int rc = checkFrame(frame);
     if (rc != DODRT_OK) return rc;
@@ -957,15 +1005,17 @@ int dodrt_trace_frame(dodrt_scene *s, const dodrt_frame *frame, const float *xs,
     if (e != cudaSuccess) return fail(DODRT_E_CUDA, "dodrt_trace_frame: %s", cudaGetErrorString(e));
     return DODRT_OK;
 }
+DODRT_CATCH
 
 int dodrt_trace_primary(dodrt_scene *s, const dodrt_frame *frame, const float *xs, const float *ys, dodrt_hit *hits)
-{
+try {
     return dodrt_trace_frame(s, frame, xs, ys, nullptr, 0, hits, nullptr);
 }
+DODRT_CATCH
 
 int dodrt_trace_shadow(dodrt_scene *s, const dodrt_frame *frame, const float *xs, const float *ys,
                        const dodrt_hit *hits, const float light[3], uint8_t *visible)
-{
+try {
     if (!s) return fail(DODRT_E_INVALID, "scene is NULL");
     int rc = checkFrame(frame);
     if (rc != DODRT_OK) return rc;
@@ -1002,12 +1052,13 @@ int dodrt_trace_shadow(dodrt_scene *s, const dodrt_frame *frame, const float *xs
     if (e != cudaSuccess) return fail(DODRT_E_CUDA, "dodrt_trace_shadow: %s", cudaGetErrorString(e));
     return DODRT_OK;
 }
+DODRT_CATCH
 
 // ---- shading + bounce loop ----------------------------------------------------------------
 
 int dodrt_render(dodrt_scene *s, const dodrt_frame *frame, const float *xs, const float *ys, const float *lights,
                  uint32_t num_lights, uint32_t depth, uint8_t *rgb)
-{
+try {
     if (!s) return fail(DODRT_E_INVALID, "scene is NULL");
     int rc = checkFrame(frame);
     if (rc != DODRT_OK) return rc;
@@ -1083,20 +1134,22 @@ int dodrt_render(dodrt_scene *s, const dodrt_frame *frame, const float *xs, cons
     if (e != cudaSuccess) return fail(DODRT_E_CUDA, "dodrt_render: %s", cudaGetErrorString(e));
     return DODRT_OK;
 }
+DODRT_CATCH
 
 // ---- frame helpers ------------------------------------------------------------------------------
 
 int dodrt_frame_local_pixels(const dodrt_frame *frame, uint64_t *slots)
-{
+try {
     int rc = checkFrame(frame);
     if (rc != DODRT_OK) return rc;
     if (!slots) return fail(DODRT_E_INVALID, "slots is NULL");
     *slots = frameSlots(frame);
     return DODRT_OK;
 }
+DODRT_CATCH
 
 int dodrt_frame_pixel_map(const dodrt_frame *f, uint32_t *pixel_of_slot, uint64_t slots)
-{
+try {
     int rc = checkFrame(f);
     if (rc != DODRT_OK) return rc;
     if (!pixel_of_slot && slots) return fail(DODRT_E_INVALID, "pixel_of_slot is NULL");
@@ -1116,12 +1169,14 @@ int dodrt_frame_pixel_map(const dodrt_frame *f, uint32_t *pixel_of_slot, uint64_
     }
     return DODRT_OK;
 }
+DODRT_CATCH
 
 int dodrt_scene_launch_count(dodrt_scene *s, uint64_t *launches)
-{
+try {
     if (!s || !launches) return fail(DODRT_E_INVALID, "NULL argument");
     *launches = s->launches.load();
     return DODRT_OK;
 }
+DODRT_CATCH
 
 } // extern "C"

@@ -400,17 +400,22 @@ __device__ __forceinline__ bool analytic_chain(const DeviceScene &s, uint32_t cl
                                                const float d[3], bool any, float &clip, Hit &hit, bool &found)
 {
     Hit h;
+    // The culling BVHs are only proven equivalent to the reference's brute force for unit-length directions
+    // (dodrt_prim_bvh.cuh: the bound on the sphere test's d2 assumes |D| = 1; with |D|^2 = 1 + delta the accepted
+    // line distance grows to r + sqrt(1e-6 + |delta|) |L|, which the node padding covers for |delta| <= 4e-6).
+    // dodrt_ray.d need not be normalised, so any other ray takes the reference's own loop over every lane.
+    const bool unitDir = fabsf(dot3(d[0], d[1], d[2], d[0], d[1], d[2]) - 1.0f) <= 2e-6f;
     if ((classes & DODRT_CLS_SPHERE) && s.num_spheres &&
-        (s.sphere_bvh ? prim_bvh_query<DODRT_KIND_SPHERE>(s.sphere_bvh, s.sphere_bvh_ids, s.sphere_lanes, o, d, any, clip, h)
-                      : sphere_query(s, o, d, any, clip, h))) {
+        ((s.sphere_bvh && unitDir) ? prim_bvh_query<DODRT_KIND_SPHERE>(s.sphere_bvh, s.sphere_bvh_ids, s.sphere_lanes, o, d, any, clip, h)
+                                   : sphere_query(s, o, d, any, clip, h))) {
         hit = h;
         found = true;
         if (any) return true;
         clip = h.t;
     }
     if ((classes & DODRT_CLS_BOX) && s.num_boxes &&
-        (s.box_bvh ? prim_bvh_query<DODRT_KIND_BOX>(s.box_bvh, s.box_bvh_ids, s.box_lanes, o, d, any, clip, h)
-                   : box_query(s, o, d, any, clip, h))) {
+        ((s.box_bvh && unitDir) ? prim_bvh_query<DODRT_KIND_BOX>(s.box_bvh, s.box_bvh_ids, s.box_lanes, o, d, any, clip, h)
+                                : box_query(s, o, d, any, clip, h))) {
         hit = h;
         found = true;
         if (any) return true;

@@ -18,6 +18,13 @@
 // the slab test itself.  The same pad covers the box primitives (their own slab test is accurate to a few e).
 // Distance pruning for closest-hit queries uses the same pad.  tests/test_gpu_parity.py and
 // tests/test_gpu_fuzz.py compare against the brute-force oracle bit for bit.
+//
+// CONTRACT: the bound above needs |D| = 1 (tca = L.D is only the projection length then; with |D|^2 = 1 + delta the
+// reference's d2 = distSq - tca^2 is off the geometric value by delta * tca^2 and a far-away sphere can be accepted).
+// dodrt_ray.d is not required to be normalised (include/dodrt.h), so the kernels use this structure only for rays
+// with | |D|^2 - 1 | <= 2e-6 (every normalised fp32 direction; the pad then still covers the bound twice) and
+// run the reference's brute-force loop for all others (analytic_chain, dodrt_kernels.cu).  Primitives with NaN / inf
+// coordinates or radii have no box: the upload then skips the structure for that class altogether.
 #pragma once
 #include "dodrt_device.cuh"
 

@@ -21,6 +21,12 @@ def upload(scene, device=0) -> capi.Scene:
     return g
 
 
+def oracle_scene(hs):
+    """dod_raytracer_b200.host.HostScene (after build_tree) -> oracle_api.Scene over copies of its arrays."""
+    from oracle_api import Scene
+    return Scene.from_host_arrays(hs.arrays())
+
+
 def assert_hits_equal(got: np.ndarray, want: np.ndarray, rays=None, what=""):
     """Bit-exact comparison of dodrt_hit arrays; any-hit rays compare hit/miss only."""
     assert len(got) == len(want)

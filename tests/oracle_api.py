@@ -99,6 +99,21 @@ class Scene:
         self.plane_lanes = pack_lanes(self.planes)
         self.box_lanes = pack_lanes(self.boxes)
 
+    @classmethod
+    def from_host_arrays(cls, a: dict) -> "Scene":
+        """Scene from the arrays dod_raytracer_b200.host.HostScene.arrays() exports (already in lane layout)."""
+        s = cls.__new__(cls)
+        s.nodes = np.ascontiguousarray(a["nodes"], np.uint64)
+        s.tri_lanes = np.ascontiguousarray(a["tri_lanes"], np.float32).reshape(-1, 72)
+        s.bounds = np.ascontiguousarray(a["bounds"], np.float32)
+        s.sphere_lanes, s.plane_lanes, s.box_lanes = a["sphere_lanes"], a["plane_lanes"], a["box_lanes"]
+        s.spheres = np.zeros((a["num_spheres"], 4), np.float32)  # only the counts are read below
+        s.planes = np.zeros((a["num_planes"], 6), np.float32)
+        s.boxes = np.zeros((a["num_boxes"], 6), np.float32)
+        s.cylinders = np.ascontiguousarray(a["cylinders"]).view(CYL_DT)
+        s.epsilon = float(a["epsilon"])
+        return s
+
     def orc(self) -> _OrcScene:
         s = _OrcScene()
         s.nodes, s.num_nodes = _ptr(self.nodes), len(self.nodes)

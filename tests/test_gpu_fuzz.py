@@ -101,6 +101,14 @@ def test_sphere_box_culling_bvh_is_exact(oracle, seed, count, scale):
     boxes[5::120, 3:] += np.float32(4 * scale)
     scene = Scene(spheres=spheres, boxes=boxes)
     rays = random_rays(rng, 60000, scale, c)
+    # dodrt_ray.d need not be normalised (include/dodrt.h): with |D| != 1 the reference's sphere arithmetic
+    # (tca = L.D, d2 = |L|^2 - tca^2, sphere.cpp:62-90) accepts spheres the geometric line misses, which a culling
+    # structure would skip -- such rays must get the brute-force answer too.  Lengths 1e-3 .. 1e3, a hair off 1, 0.
+    loose = random_rays(rng, 30000, scale, c)
+    f = np.float32(10.0) ** rng.uniform(-3, 3, len(loose)).astype(np.float32)
+    f[::4] = np.float32(1.0) + rng.uniform(-1e-3, 1e-3, len(f[::4])).astype(np.float32)
+    f[1::64] = 0.0
+    loose["d"] = (loose["d"] * f[:, None]).astype(np.float32)
     with capi.Scene(0) as g:
         g.set_spheres(scene.sphere_lanes, count)
         g.set_boxes(scene.box_lanes, count)
@@ -108,3 +116,13 @@ def test_sphere_box_culling_bvh_is_exact(oracle, seed, count, scale):
             want = oracle.intersect(scene, rays, cls, nthreads=8)
             assert_hits_equal(g.intersect(rays, cls), want, rays=rays, what=f"seed {seed} classes {cls}")
             assert (want["prim"] != 0xFFFFFFFF).mean() > 0.02
+            want = oracle.intersect(scene, loose, cls, nthreads=8)
+            assert_hits_equal(g.intersect(loose, cls), want, rays=loose, what=f"seed {seed} classes {cls} un-normalised")
+    # a NaN / inf primitive cannot be boxed: the class falls back to the reference's loop, answers unchanged
+    bad = spheres.copy()
+    bad[5, 0], bad[9, 3] = np.nan, np.inf
+    bscene = Scene(spheres=bad, boxes=boxes)
+    with capi.Scene(0) as g:
+        g.set_spheres(bscene.sphere_lanes, count)
+        want = oracle.intersect(bscene, rays[:20000], CLS_SPHERE, nthreads=8)
+        assert_hits_equal(g.intersect(rays[:20000], CLS_SPHERE), want, rays=rays[:20000], what=f"seed {seed} NaN sphere")

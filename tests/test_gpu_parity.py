@@ -336,11 +336,14 @@ def test_donated_rays_resume_bit_identically(monkeypatch, oracle):
     assert got.tobytes() == want.tobytes()
 
 
-def test_concurrent_donating_launches(oracle):
-    """Four host threads trace frames with the donating kernel (variant 7) at the same time, each on its own CUDA
+@pytest.mark.parametrize("nthreads", [4, 8])
+def test_concurrent_donating_launches(oracle, nthreads):
+    """Several host threads trace frames with the donating kernel (variant 7) at the same time, each on its own CUDA
     stream: the grids together exceed what the GPU can keep resident, so blocks of one launch start only when blocks
     of another retire.  The helper loop must not wait for blocks that have not started (it counts warps at kernel
-    entry); every call has to return, with the single-launch bits."""
+    entry); every call has to return, with the single-launch bits.  The threads issue their FIRST launch on a fresh
+    scene together (barrier): that is when the persistent donation queues are created and handed out, and a queue
+    must never serve two launches in flight (8 threads > 4 queues: the rest take the per-launch pool path)."""
     import threading
     import torch
     from dod_raytracer_b200 import host
@@ -351,16 +354,20 @@ def test_concurrent_donating_launches(oracle):
     dev = torch.device("cuda:0")
     d_xs, d_ys = torch.from_numpy(xs).to(dev), torch.from_numpy(ys).to(dev)
     light = np.asarray(LIGHT0, np.float32)
+    with upload(scene) as g0:
+        g0.set_kernel_variant(3)
+        want_hits, want_vis = g0.trace_frame(frame, xs, ys, LIGHT0[None, :])
     with upload(scene) as g:
         g.set_kernel_variant(7)
-        want_hits, want_vis = g.trace_frame(frame, xs, ys, LIGHT0[None, :])
         results, errors = {}, []
+        gate = threading.Barrier(nthreads)
 
         def work(k):
             try:
                 st = torch.cuda.Stream(device=dev)
                 d_hits = torch.empty((w * h, 16), dtype=torch.uint8, device=dev)
                 d_vis = torch.empty(w * h, dtype=torch.uint8, device=dev)
+                gate.wait(timeout=60)
                 for rep in range(8):
                     g.trace_primary_device(frame, d_xs.data_ptr(), d_ys.data_ptr(), d_hits.data_ptr(), st.cuda_stream)
                     g.trace_shadow_device(frame, d_xs.data_ptr(), d_ys.data_ptr(), d_hits.data_ptr(), light, d_vis.data_ptr(),
@@ -370,14 +377,14 @@ def test_concurrent_donating_launches(oracle):
             except Exception as e:  # noqa: BLE001
                 errors.append(e)
 
-        threads = [threading.Thread(target=work, args=(k,), daemon=True) for k in range(4)]
+        threads = [threading.Thread(target=work, args=(k,), daemon=True) for k in range(nthreads)]
         for t in threads:
             t.start()
         for t in threads:
             t.join(timeout=120)
             assert not t.is_alive(), "a donating launch did not return (helpers waiting for non-resident blocks?)"
         assert not errors, errors
-        assert len(results) == 4
+        assert len(results) == nthreads
         for k, (hits, vis) in results.items():
             assert hits == want_hits.tobytes(), k
             assert vis == want_vis[0].tobytes(), k
