@@ -37,7 +37,11 @@ EXPORTED_SYMBOLS = [
     "dodrt_intersect", "dodrt_trace_primary", "dodrt_trace_shadow", "dodrt_trace_frame",
     "dodrt_intersect_device", "dodrt_trace_primary_device", "dodrt_trace_shadow_device",
     "dodrt_frame_assemble_device", "dodrt_frame_local_pixels", "dodrt_frame_pixel_map", "dodrt_scene_launch_count",
+    "dodrt_trace_frame_device", "dodrt_frame_buffer_create", "dodrt_frame_buffer_export", "dodrt_frame_buffer_open",
+    "dodrt_frame_buffer_attach", "dodrt_frame_buffer_pointers", "dodrt_frame_buffer_destroy",
+    "dodrt_multi_create", "dodrt_multi_trace_frame", "dodrt_multi_destroy",
 ]
+ABI_VERSION = 2
 
 
 class DodrtError(RuntimeError):
@@ -86,7 +90,7 @@ def load() -> C.CDLL:
     lib.dodrt_last_error.restype = C.c_char_p
     for name in EXPORTED_SYMBOLS:
         getattr(lib, name)  # AttributeError if the ABI is incomplete
-    if lib.dodrt_abi_version() != 1:
+    if lib.dodrt_abi_version() != ABI_VERSION:
         raise ImportError(f"unexpected dodrt ABI version {lib.dodrt_abi_version()}")
     _lib = lib
     return lib
@@ -264,7 +268,127 @@ class Scene:
                                                      C.c_uint64(slots_per_rank), C.c_void_p(d_hits_out),
                                                      C.c_void_p(d_vis_out) if d_vis_out else None, C.c_void_p(stream)))
 
+    def trace_frame_device(self, frame: Frame, d_xs: int, d_ys: int, lights, d_hits: int, d_visible: int,
+                           mirror: "Optional[FrameBuffer]" = None, stream: int = 0):
+        """dodrt_trace_frame_device: primary + shadow queues of this call's tiles in one launch; `mirror` = a frame
+        buffer view for this scene's GPU that also receives every result (row-major)."""
+        lights = np.ascontiguousarray(lights, np.float32).reshape(-1, 3)
+        _check(self._lib.dodrt_trace_frame_device(self._h, C.byref(frame), C.c_void_p(d_xs), C.c_void_p(d_ys), _ptr(lights),
+                                                  C.c_uint32(len(lights)), C.c_void_p(d_hits),
+                                                  C.c_void_p(d_visible) if d_visible else None,
+                                                  mirror._h if mirror is not None else None, C.c_void_p(stream)))
+
     def launch_count(self) -> int:
         n = C.c_uint64(0)
         _check(self._lib.dodrt_scene_launch_count(self._h, C.byref(n)))
         return n.value
+
+
+class FrameBufferDesc(C.Structure):
+    """``dodrt_frame_buffer_desc``: what another process needs to open a frame buffer (96 bytes, plain data)."""
+
+    _fields_ = [("width", C.c_uint32), ("height", C.c_uint32), ("num_lights", C.c_uint32), ("device", C.c_uint32),
+                ("bytes", C.c_uint64), ("ipc_handle", C.c_uint8 * 64), ("reserved", C.c_uint8 * 8)]
+
+    def to_bytes(self) -> bytes:
+        return bytes(self)
+
+    @classmethod
+    def from_bytes(cls, raw: bytes) -> "FrameBufferDesc":
+        return cls.from_buffer_copy(raw)
+
+
+class FrameBuffer:
+    """``dodrt_frame_buffer``: a row-major frame in one GPU's HBM that kernels on other GPUs write into over NVLink.
+    ``FrameBuffer.create(scene, ...)`` on the owner; ``attach`` (same process) / ``open`` (other process) elsewhere."""
+
+    def __init__(self, handle, keepalive=None):
+        self._lib = load()
+        self._h = handle
+        self._keep = keepalive
+
+    @classmethod
+    def create(cls, owner: Scene, width: int, height: int, num_lights: int) -> "FrameBuffer":
+        h = C.c_void_p()
+        _check(load().dodrt_frame_buffer_create(owner._h, C.c_uint32(width), C.c_uint32(height), C.c_uint32(num_lights),
+                                                C.byref(h)))
+        return cls(h, owner)
+
+    @classmethod
+    def attach(cls, user: Scene, owner_fb: "FrameBuffer") -> "FrameBuffer":
+        h = C.c_void_p()
+        _check(load().dodrt_frame_buffer_attach(user._h, owner_fb._h, C.byref(h)))
+        return cls(h, (user, owner_fb))
+
+    @classmethod
+    def open(cls, user: Scene, desc: FrameBufferDesc) -> "FrameBuffer":
+        h = C.c_void_p()
+        _check(load().dodrt_frame_buffer_open(user._h, C.byref(desc), C.byref(h)))
+        return cls(h, user)
+
+    def export(self) -> FrameBufferDesc:
+        d = FrameBufferDesc()
+        _check(self._lib.dodrt_frame_buffer_export(self._h, C.byref(d)))
+        return d
+
+    def pointers(self):
+        """(device address of the hit records, device address of the visibility bytes or 0)"""
+        hits, vis = C.c_void_p(), C.c_void_p()
+        _check(self._lib.dodrt_frame_buffer_pointers(self._h, C.byref(hits), C.byref(vis)))
+        return hits.value or 0, vis.value or 0
+
+    def close(self):
+        if getattr(self, "_h", None) is not None and self._h:
+            self._lib.dodrt_frame_buffer_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+
+class Multi:
+    """``dodrt_multi``: one frame traced by several GPUs of this process, results in ONE host frame."""
+
+    def __init__(self, scenes):
+        self._lib = load()
+        self._scenes = list(scenes)
+        arr = (C.c_void_p * len(self._scenes))(*[s._h for s in self._scenes])
+        self._h = C.c_void_p()
+        _check(self._lib.dodrt_multi_create(arr, C.c_uint32(len(self._scenes)), C.byref(self._h)))
+
+    def trace_frame(self, frame: Frame, xs, ys, lights, hits_out: Optional[np.ndarray] = None,
+                    vis_out: Optional[np.ndarray] = None):
+        xs, ys = np.ascontiguousarray(xs, np.float32), np.ascontiguousarray(ys, np.float32)
+        lights = np.ascontiguousarray(lights, np.float32).reshape(-1, 3)
+        n = frame.width * frame.height
+        hits = hits_out if hits_out is not None else np.empty(n, HIT_DT)
+        vis = vis_out if vis_out is not None else np.empty((len(lights), n), np.uint8)
+        _check(self._lib.dodrt_multi_trace_frame(self._h, C.byref(frame), _ptr(xs), _ptr(ys), _ptr(lights),
+                                                 C.c_uint32(len(lights)), _ptr(hits), _ptr(vis)))
+        return hits, vis
+
+    def close(self):
+        if getattr(self, "_h", None) is not None and self._h:
+            self._lib.dodrt_multi_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()

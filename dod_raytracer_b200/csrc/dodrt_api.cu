@@ -14,6 +14,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <memory>
 #include <mutex>
 #include <new>
 #include <string>
@@ -127,6 +128,31 @@ struct dodrt_scene {
     bool donateBusy[kDonateQueues] = {false, false, false, false};
     cudaStream_t donateOwner[kDonateQueues] = {nullptr, nullptr, nullptr, nullptr}; // stream of the launch that used it last
     std::atomic<uint32_t> donateEpoch{0};
+    // Host-buffer entry points (dodrt_trace_frame & co): they run on the scene's own stream one call at a time
+    // (hostMutex), so their staging memory and fence events are PERSISTENT -- grown on demand, never freed before the
+    // scene is: a per-frame call pays for no allocation, no event creation and no pool bookkeeping.
+    std::mutex hostMutex;
+    float *stTables = nullptr;
+    size_t stTablesBytes = 0;
+    dodrt_hit *stHits = nullptr;
+    size_t stHitsBytes = 0;
+    uint8_t *stVis = nullptr;
+    size_t stVisBytes = 0;
+    std::vector<cudaEvent_t> stEvents;
+    size_t stEventsUsed = 0;
+};
+
+// dodrt_frame_buffer: a row-major frame in one GPU's HBM that kernels on other GPUs write into (include/dodrt.h)
+struct dodrt_frame_buffer {
+    int device = 0;      // GPU whose kernels use this view (owner: where the memory lives)
+    int ownerDevice = 0;
+    bool owner = false;  // allocated here (cudaFree) ...
+    bool ipc = false;    // ... or opened from another process (cudaIpcCloseMemHandle); neither = same-process peer view
+    uint32_t width = 0, height = 0, numLights = 0;
+    size_t bytes = 0;
+    char *base = nullptr;
+    dodrt_hit *hits() const { return reinterpret_cast<dodrt_hit *>(base); }
+    uint8_t *visible() const { return reinterpret_cast<uint8_t *>(base + (size_t)width * height * sizeof(dodrt_hit)); }
 };
 
 namespace {
@@ -293,16 +319,29 @@ cudaError_t launchTraceOn(dodrt_scene *s, TraceMode mode, const TraceParams &p, 
     return e != cudaSuccess ? e : er;
 }
 
+// Second destination of a frame pass's results, written by the kernels themselves (TraceParams::mirror_*): a peer GPU's
+// frame buffer (by pixel) or the caller's pinned host buffers (same layout as the device results).
+struct Mirror {
+    dodrt_hit *hits = nullptr;
+    uint8_t *visible = nullptr; // of the light the pass handles (two-launch path) / of light 0 (fused path)
+    uint64_t lightStride = 0;
+    uint32_t byPixel = 0;
+};
+
 // Traces local tiles [tileBegin, tileBegin + tileCount) of the frame (tileCount is clamped); d_hits / d_visible
 // always point at slot 0 of the call's result buffers.
 int launchFrame(dodrt_scene *s, TraceMode mode, const dodrt_frame *frame, const float *d_xs, const float *d_ys,
                 dodrt_hit *d_hits, const float *light, uint8_t *d_visible, cudaStream_t stream, uint32_t tileBegin = 0,
-                uint32_t tileCount = 0xFFFFFFFFu)
+                uint32_t tileCount = 0xFFFFFFFFu, const Mirror *mirror = nullptr)
 {
     TraceParams p{};
     p.scene = s->dev;
     p.classes = frame->classes;
     p.frame = *frame;
+    if (mirror) {
+        p.mirror_by_pixel = mirror->byPixel;
+        p.mirror_light_stride = mirror->lightStride;
+    }
     uint32_t localTiles;
     frameTiles(frame, &p.tiles_x, &localTiles);
     if (tileBegin >= localTiles) {
@@ -317,6 +356,11 @@ int launchFrame(dodrt_scene *s, TraceMode mode, const dodrt_frame *frame, const 
     p.xs = d_xs;
     p.ys = d_ys;
     p.visible = d_visible ? d_visible + slotBase : nullptr;
+    if (mirror) { // by pixel: absolute indices; else the mirror has the layout of the local buffers
+        const uint64_t mbase = mirror->byPixel ? 0 : slotBase;
+        p.mirror_hits = (mode == kModePrimary && mirror->hits) ? mirror->hits + mbase : nullptr;
+        p.mirror_visible = (mode == kModeShadow && mirror->visible) ? mirror->visible + mbase : nullptr;
+    }
     if (light) {
         p.light[0] = light[0];
         p.light[1] = light[1];
@@ -360,6 +404,135 @@ int launchFrame(dodrt_scene *s, TraceMode mode, const dodrt_frame *frame, const 
     if (le != cudaSuccess) return fail(DODRT_E_CUDA, "kernel launch failed: %s", cudaGetErrorString(le));
     s->launches.fetch_add(1);
     return DODRT_OK;
+}
+
+
+// Primary + shadow queues of the frame share in ONE launch (trace_frame_kernel).  d_visible: [num_lights][visStride].
+// Returns DODRT_OK with *done = false when the selected kernel variant has no fused form (A/B variants): the caller
+// then runs the separate passes.
+int launchFrameFused(dodrt_scene *s, const dodrt_frame *frame, const float *d_xs, const float *d_ys, const float *lights,
+                     uint32_t numLights, dodrt_hit *d_hits, uint8_t *d_visible, uint64_t visStride, const Mirror *mirror,
+                     cudaStream_t stream, bool *done)
+{
+    *done = false;
+    const char *fusedEnv = std::getenv("DODRT_FUSED"); // A/B knob, read per call: 0 = separate primary / shadow launches
+    const bool fusedOn = !fusedEnv || std::atoi(fusedEnv) != 0;
+    if (!fusedOn || numLights > (uint32_t)kMaxLights) return DODRT_OK;
+    TraceParams p{};
+    p.scene = s->dev;
+    p.classes = frame->classes;
+    p.frame = *frame;
+    uint32_t tiles;
+    frameTiles(frame, &p.tiles_x, &tiles);
+    const uint64_t tilePixels = (uint64_t)frame->tile_w * frame->tile_h;
+    p.count = tiles * tilePixels;
+    p.shadow_count = p.count * numLights;
+    if (p.count == 0) {
+        *done = true;
+        return DODRT_OK;
+    }
+    // donation pays when the whole job is only a few batches per warp (see resolve_variant)
+    p.variant = resolve_variant(s->variant, s->cfg[kDonateVariant][kModeFrame], p.count + p.shadow_count, frame->tile_stride > 1,
+                                s->dev.num_nodes >= kBigTreeNodes);
+    if (p.variant != kDefaultVariant && p.variant != kDonateVariant) return DODRT_OK;
+    p.hits = d_hits;
+    p.visible = d_visible;
+    p.visible_light_stride = visStride;
+    p.xs = d_xs;
+    p.ys = d_ys;
+    p.num_lights = numLights;
+    for (uint32_t l = 0; l < numLights; l++) {
+        for (int k = 0; k < 3; k++) p.lights[l][k] = lights[3 * l + k];
+    }
+    if (mirror) {
+        p.mirror_hits = mirror->hits;
+        p.mirror_visible = numLights ? mirror->visible : nullptr;
+        p.mirror_light_stride = mirror->lightStride;
+        p.mirror_by_pixel = mirror->byPixel;
+    }
+    int rc = ensurePool(s);
+    if (rc != DODRT_OK) return rc;
+    // one stream-ordered block: counters | tile_done | ready_queue | tile_order, the first three zeroed by one memset
+    static const bool orderTiles = [] { const char *e = std::getenv("DODRT_TILE_ORDER"); return !e || std::atoi(e) != 0; }();
+    const bool order = orderTiles && (frame->classes & DODRT_CLS_TREE) && s->dev.num_nodes != 0 && tiles >= 64;
+    const size_t counterBytes = sizeof(unsigned long long) * kCounterWords;
+    const size_t tileBytes = sizeof(uint32_t) * (size_t)tiles;
+    char *block = nullptr;
+    CUDA_TRY(cudaMallocFromPoolAsync(&block, counterBytes + tileBytes * (order ? 3 : 2), s->pool, stream));
+    cudaError_t e = cudaMemsetAsync(block, 0, counterBytes + 2 * tileBytes, stream);
+    p.counter = reinterpret_cast<unsigned long long *>(block);
+    p.tile_done = reinterpret_cast<uint32_t *>(block + counterBytes);
+    p.ready_queue = p.tile_done + tiles;
+    p.tile_order = order ? p.ready_queue + tiles : nullptr;
+    p.num_local_tiles = tiles;
+    if (e == cudaSuccess) e = launchTraceOn(s, kModeFrame, p, stream);
+    cudaFreeAsync(block, stream);
+    if (e != cudaSuccess) return fail(DODRT_E_CUDA, "fused frame launch failed: %s", cudaGetErrorString(e));
+    s->launches.fetch_add(order ? 2 : 1);
+    *done = true;
+    return DODRT_OK;
+}
+
+// The whole frame share: fused launch when the variant has one, else primary pass + one shadow pass per light.
+int traceFrameOnDevice(dodrt_scene *s, const dodrt_frame *frame, const float *d_xs, const float *d_ys, const float *lights,
+                       uint32_t numLights, dodrt_hit *d_hits, uint8_t *d_visible, uint64_t visStride, const Mirror *mirror,
+                       cudaStream_t stream)
+{
+    bool done = false;
+    int rc = launchFrameFused(s, frame, d_xs, d_ys, lights, numLights, d_hits, d_visible, visStride, mirror, stream, &done);
+    if (rc != DODRT_OK || done) return rc;
+    rc = launchFrame(s, kModePrimary, frame, d_xs, d_ys, d_hits, nullptr, nullptr, stream, 0, 0xFFFFFFFFu, mirror);
+    for (uint32_t l = 0; l < numLights && rc == DODRT_OK; l++) {
+        Mirror m;
+        if (mirror) {
+            m = *mirror;
+            m.visible = mirror->visible ? mirror->visible + (uint64_t)l * mirror->lightStride : nullptr;
+        }
+        rc = launchFrame(s, kModeShadow, frame, d_xs, d_ys, d_hits, lights + 3 * l, d_visible + (uint64_t)l * visStride, stream, 0,
+                         0xFFFFFFFFu, mirror ? &m : nullptr);
+    }
+    return rc;
+}
+
+// Is [ptr, ptr + bytes) pinned host memory the scene's GPU can write to?  Returns its device-side address then.
+void *mappedHostPointer(const void *ptr, size_t bytes)
+{
+    if (!ptr || !bytes) return nullptr;
+    cudaPointerAttributes a{}, b{};
+    if (cudaPointerGetAttributes(&a, ptr) != cudaSuccess ||
+        cudaPointerGetAttributes(&b, static_cast<const char *>(ptr) + bytes - 1) != cudaSuccess) {
+        cudaGetLastError();
+        return nullptr;
+    }
+    if (a.type != cudaMemoryTypeHost || b.type != cudaMemoryTypeHost || !a.devicePointer) return nullptr;
+    return a.devicePointer;
+}
+
+// grow-only staging of the host-buffer entry points (dodrt_scene::hostMutex held)
+template <typename T> cudaError_t growStaging(T *&ptr, size_t &have, size_t need)
+{
+    if (need <= have) return cudaSuccess;
+    if (ptr) cudaFree(ptr);
+    ptr = nullptr;
+    have = 0;
+    const size_t bytes = need + need / 8; // head room: a slightly larger frame does not re-allocate
+    cudaError_t e = cudaMalloc(&ptr, bytes);
+    if (e == cudaSuccess) have = bytes;
+    return e;
+}
+
+// `to` waits for what `from` has queued so far; events are pre-created and recycled call after call
+cudaError_t stagingFence(dodrt_scene *s, cudaStream_t from, cudaStream_t to)
+{
+    if (s->stEventsUsed == s->stEvents.size()) {
+        cudaEvent_t ev = nullptr;
+        cudaError_t e = cudaEventCreateWithFlags(&ev, cudaEventDisableTiming);
+        if (e != cudaSuccess) return e;
+        s->stEvents.push_back(ev);
+    }
+    cudaEvent_t ev = s->stEvents[s->stEventsUsed++];
+    cudaError_t e = cudaEventRecord(ev, from);
+    return e == cudaSuccess ? cudaStreamWaitEvent(to, ev, 0) : e;
 }
 
 } // namespace
@@ -434,6 +607,10 @@ try {
     if (s->stream) cudaStreamDestroy(s->stream);
     if (s->copyStream) cudaStreamDestroy(s->copyStream);
     if (s->pool) cudaMemPoolDestroy(s->pool);
+    for (cudaEvent_t ev : s->stEvents) cudaEventDestroy(ev);
+    if (s->stTables) cudaFree(s->stTables);
+    if (s->stHits) cudaFree(s->stHits);
+    if (s->stVis) cudaFree(s->stVis);
     for (int q = 0; q < dodrt_scene::kDonateQueues; q++) {
         if (s->donateDone[q]) cudaEventDestroy(s->donateDone[q]);
         if (s->donateQueue[q]) cudaFree(s->donateQueue[q]);
@@ -869,6 +1046,168 @@ try {
 }
 DODRT_CATCH
 
+int dodrt_trace_frame_device(dodrt_scene *s, const dodrt_frame *frame, const float *d_xs, const float *d_ys, const float *lights,
+                             uint32_t num_lights, dodrt_hit *d_hits, uint8_t *d_visible, dodrt_frame_buffer *mirror, void *stream)
+try {
+    if (!s) return fail(DODRT_E_INVALID, "scene is NULL");
+    int rc = checkFrame(frame);
+    if (rc != DODRT_OK) return rc;
+    if (!d_xs || !d_ys || !d_hits) return fail(DODRT_E_INVALID, "NULL table/hit buffer");
+    if (num_lights && (!lights || !d_visible)) return fail(DODRT_E_INVALID, "NULL lights/visible buffer");
+    if (num_lights > (uint32_t)kMaxLights) return fail(DODRT_E_LIMIT, "%u lights exceed the limit of %d", num_lights, kMaxLights);
+    Mirror m;
+    if (mirror) {
+        if (mirror->device != s->device) {
+            return fail(DODRT_E_INVALID, "frame buffer view belongs to device %d, the scene to device %d (open / attach it for this scene)",
+                        mirror->device, s->device);
+        }
+        if (mirror->width != frame->width || mirror->height != frame->height || mirror->numLights < num_lights) {
+            return fail(DODRT_E_INVALID, "frame buffer is %ux%u with %u lights, the frame %ux%u with %u", mirror->width,
+                        mirror->height, mirror->numLights, frame->width, frame->height, num_lights);
+        }
+        m.hits = mirror->hits();
+        m.visible = mirror->visible();
+        m.lightStride = (uint64_t)mirror->width * mirror->height;
+        m.byPixel = 1;
+    }
+    DeviceGuard guard(s->device);
+    if (!guard.ok) return fail(DODRT_E_CUDA, "cannot select device %d", s->device);
+    const uint64_t slots = frame->compact ? frameSlots(frame) : (uint64_t)frame->width * frame->height;
+    return traceFrameOnDevice(s, frame, d_xs, d_ys, lights, num_lights, d_hits, d_visible, slots, mirror ? &m : nullptr,
+                              static_cast<cudaStream_t>(stream));
+}
+DODRT_CATCH
+
+// ---- frame buffers other GPUs write into -------------------------------------------------------------
+
+int dodrt_frame_buffer_create(dodrt_scene *owner, uint32_t width, uint32_t height, uint32_t num_lights, dodrt_frame_buffer **fb)
+try {
+    if (!owner || !fb) return fail(DODRT_E_INVALID, "NULL argument");
+    *fb = nullptr;
+    if (!width || !height || (uint64_t)width * height >= 0xFFFFFFFFull) return fail(DODRT_E_INVALID, "bad frame size %ux%u", width, height);
+    if (num_lights > (uint32_t)kMaxLights) return fail(DODRT_E_LIMIT, "%u lights exceed the limit of %d", num_lights, kMaxLights);
+    DeviceGuard guard(owner->device);
+    if (!guard.ok) return fail(DODRT_E_CUDA, "cannot select device %d", owner->device);
+    std::unique_ptr<dodrt_frame_buffer> f(new dodrt_frame_buffer());
+    f->device = f->ownerDevice = owner->device;
+    f->owner = true;
+    f->width = width, f->height = height, f->numLights = num_lights;
+    f->bytes = (size_t)width * height * (sizeof(dodrt_hit) + num_lights);
+    // plain cudaMalloc (not a pool): the allocation must be exportable with cudaIpcGetMemHandle
+    CUDA_TRY(cudaMalloc(&f->base, f->bytes));
+    cudaError_t e = cudaMemset(f->base, 0xFF, (size_t)width * height * sizeof(dodrt_hit)); // "miss" until written
+    if (e == cudaSuccess && num_lights) e = cudaMemset(f->visible(), 0, (size_t)width * height * num_lights);
+    if (e != cudaSuccess) {
+        cudaFree(f->base);
+        return fail(DODRT_E_CUDA, "frame buffer: %s", cudaGetErrorString(e));
+    }
+    *fb = f.release();
+    return DODRT_OK;
+}
+DODRT_CATCH
+
+int dodrt_frame_buffer_export(dodrt_frame_buffer *fb, dodrt_frame_buffer_desc *desc)
+try {
+    if (!fb || !desc) return fail(DODRT_E_INVALID, "NULL argument");
+    if (!fb->owner) return fail(DODRT_E_INVALID, "only the owner of a frame buffer can export it");
+    static_assert(sizeof(cudaIpcMemHandle_t) <= sizeof(desc->ipc_handle), "ipc handle does not fit the descriptor");
+    std::memset(desc, 0, sizeof(*desc));
+    DeviceGuard guard(fb->ownerDevice);
+    if (!guard.ok) return fail(DODRT_E_CUDA, "cannot select device %d", fb->ownerDevice);
+    cudaIpcMemHandle_t h;
+    CUDA_TRY(cudaIpcGetMemHandle(&h, fb->base));
+    std::memcpy(desc->ipc_handle, &h, sizeof(h));
+    desc->width = fb->width, desc->height = fb->height, desc->num_lights = fb->numLights;
+    desc->device = (uint32_t)fb->ownerDevice;
+    desc->bytes = fb->bytes;
+    return DODRT_OK;
+}
+DODRT_CATCH
+
+int dodrt_frame_buffer_open(dodrt_scene *user, const dodrt_frame_buffer_desc *desc, dodrt_frame_buffer **fb)
+try {
+    if (!user || !desc || !fb) return fail(DODRT_E_INVALID, "NULL argument");
+    *fb = nullptr;
+    if ((size_t)desc->width * desc->height * (sizeof(dodrt_hit) + desc->num_lights) != desc->bytes || !desc->bytes) {
+        return fail(DODRT_E_INVALID, "inconsistent frame buffer descriptor");
+    }
+    DeviceGuard guard(user->device);
+    if (!guard.ok) return fail(DODRT_E_CUDA, "cannot select device %d", user->device);
+    cudaIpcMemHandle_t h;
+    std::memcpy(&h, desc->ipc_handle, sizeof(h));
+    void *base = nullptr;
+    // maps the owner's allocation into this process; peer access from the current device is enabled on demand
+    CUDA_TRY(cudaIpcOpenMemHandle(&base, h, cudaIpcMemLazyEnablePeerAccess));
+    dodrt_frame_buffer *f = new (std::nothrow) dodrt_frame_buffer();
+    if (!f) {
+        cudaIpcCloseMemHandle(base);
+        return fail(DODRT_E_NOMEM, "out of host memory");
+    }
+    f->device = user->device;
+    f->ownerDevice = (int)desc->device;
+    f->ipc = true;
+    f->width = desc->width, f->height = desc->height, f->numLights = desc->num_lights;
+    f->bytes = desc->bytes;
+    f->base = static_cast<char *>(base);
+    *fb = f;
+    return DODRT_OK;
+}
+DODRT_CATCH
+
+int dodrt_frame_buffer_attach(dodrt_scene *user, dodrt_frame_buffer *owner_fb, dodrt_frame_buffer **fb)
+try {
+    if (!user || !owner_fb || !fb) return fail(DODRT_E_INVALID, "NULL argument");
+    *fb = nullptr;
+    if (!owner_fb->owner) return fail(DODRT_E_INVALID, "attach needs the frame buffer its owner created");
+    if (user->device != owner_fb->ownerDevice) {
+        int can = 0;
+        CUDA_TRY(cudaDeviceCanAccessPeer(&can, user->device, owner_fb->ownerDevice));
+        if (!can) return fail(DODRT_E_CUDA, "device %d cannot address the memory of device %d", user->device, owner_fb->ownerDevice);
+        DeviceGuard guard(user->device);
+        if (!guard.ok) return fail(DODRT_E_CUDA, "cannot select device %d", user->device);
+        cudaError_t e = cudaDeviceEnablePeerAccess(owner_fb->ownerDevice, 0);
+        if (e == cudaErrorPeerAccessAlreadyEnabled) {
+            cudaGetLastError();
+        } else if (e != cudaSuccess) {
+            return fail(DODRT_E_CUDA, "cudaDeviceEnablePeerAccess(%d -> %d): %s", user->device, owner_fb->ownerDevice, cudaGetErrorString(e));
+        }
+    }
+    dodrt_frame_buffer *f = new (std::nothrow) dodrt_frame_buffer(*owner_fb);
+    if (!f) return fail(DODRT_E_NOMEM, "out of host memory");
+    f->device = user->device;
+    f->owner = false;
+    f->ipc = false;
+    *fb = f;
+    return DODRT_OK;
+}
+DODRT_CATCH
+
+int dodrt_frame_buffer_pointers(dodrt_frame_buffer *fb, dodrt_hit **d_hits, uint8_t **d_visible)
+try {
+    if (!fb) return fail(DODRT_E_INVALID, "frame buffer is NULL");
+    if (d_hits) *d_hits = fb->hits();
+    if (d_visible) *d_visible = fb->numLights ? fb->visible() : nullptr;
+    return DODRT_OK;
+}
+DODRT_CATCH
+
+int dodrt_frame_buffer_destroy(dodrt_frame_buffer *fb)
+try {
+    if (!fb) return DODRT_OK;
+    if (fb->owner || fb->ipc) {
+        DeviceGuard guard(fb->owner ? fb->ownerDevice : fb->device);
+        cudaDeviceSynchronize();
+        if (fb->owner) {
+            cudaFree(fb->base);
+        } else {
+            cudaIpcCloseMemHandle(fb->base);
+        }
+    }
+    delete fb;
+    return DODRT_OK;
+}
+DODRT_CATCH
+
 // ---- host-buffer entry points -------------------------------------------------------------------
 
 int dodrt_intersect(dodrt_scene *s, const dodrt_ray *rays, uint64_t num_rays, uint32_t classes, dodrt_hit *hits)
@@ -914,40 +1253,54 @@ try {
     if (rc != DODRT_OK) return rc;
     DeviceGuard guard(s->device);
     if (!guard.ok) return fail(DODRT_E_CUDA, "cannot select device %d", s->device);
-    cudaStream_t st = s->stream;
     const uint64_t slots = frame->compact ? frameSlots(frame) : (uint64_t)frame->width * frame->height;
     if (slots == 0) return DODRT_OK;
-    float *d_tables = nullptr;
-    dodrt_hit *d_hits = nullptr;
-    uint8_t *d_vis = nullptr;
+    std::lock_guard<std::mutex> hostLock(s->hostMutex); // one host-buffer call at a time per scene: persistent staging
+    cudaStream_t st = s->stream;
+    s->stEventsUsed = 0;
     const size_t tableFloats = (size_t)frame->width + frame->height;
-    CUDA_TRY(cudaMallocFromPoolAsync(&d_tables, tableFloats * sizeof(float), s->pool, st));
-    cudaError_t e = cudaMallocFromPoolAsync(&d_hits, slots * sizeof(dodrt_hit), s->pool, st);
-    if (e == cudaSuccess && num_lights) e = cudaMallocFromPoolAsync(&d_vis, slots * (size_t)num_lights, s->pool, st);
-    if (e == cudaSuccess) e = cudaMemcpyAsync(d_tables, xs, frame->width * sizeof(float), cudaMemcpyHostToDevice, st);
+    cudaError_t e = growStaging(s->stTables, s->stTablesBytes, tableFloats * sizeof(float));
+    if (e == cudaSuccess) e = growStaging(s->stHits, s->stHitsBytes, slots * sizeof(dodrt_hit));
+    if (e == cudaSuccess) e = growStaging(s->stVis, s->stVisBytes, slots * (size_t)(num_lights ? num_lights : 1));
+    if (e != cudaSuccess) return fail(DODRT_E_CUDA, "dodrt_trace_frame staging: %s", cudaGetErrorString(e));
+    float *d_tables = s->stTables;
+    dodrt_hit *d_hits = s->stHits;
+    uint8_t *d_vis = s->stVis;
+    e = cudaMemcpyAsync(d_tables, xs, frame->width * sizeof(float), cudaMemcpyHostToDevice, st);
     if (e == cudaSuccess) {
         e = cudaMemcpyAsync(d_tables + frame->width, ys, frame->height * sizeof(float), cudaMemcpyHostToDevice, st);
+    }
+    // ---- zero-copy: the caller's buffers are pinned host memory this GPU can address.  The kernels write every result
+    // there themselves, next to the device copy the shadow queue reads (TraceParams::mirror_*): 128-byte rows of hit
+    // records stream over PCIe WHILE the frame is traced, nothing is copied afterwards, and the whole share is one fused
+    // launch.  (Full-frame results of a tile split also need the other ranks' pixels cleared: staged path below.)
+    const char *zcEnv = std::getenv("DODRT_ZEROCOPY"); // A/B knob, read per call: 0 = always stage + copy
+    const bool zeroCopyOn = !zcEnv || std::atoi(zcEnv) != 0;
+    void *mHits = zeroCopyOn ? mappedHostPointer(hits, slots * sizeof(dodrt_hit)) : nullptr;
+    void *mVis = (zeroCopyOn && num_lights) ? mappedHostPointer(visible, slots * (size_t)num_lights) : nullptr;
+    if (e == cudaSuccess && mHits && (num_lights == 0 || mVis) && (frame->compact || frame->tile_stride == 1)) {
+        Mirror m;
+        m.hits = static_cast<dodrt_hit *>(mHits);
+        m.visible = static_cast<uint8_t *>(mVis);
+        m.lightStride = slots;
+        m.byPixel = 0;
+        rc = traceFrameOnDevice(s, frame, d_tables, d_tables + frame->width, lights, num_lights, d_hits, d_vis, slots, &m, st);
+        cudaError_t es = cudaStreamSynchronize(st);
+        if (rc != DODRT_OK) return rc;
+        if (es != cudaSuccess) return fail(DODRT_E_CUDA, "dodrt_trace_frame: %s", cudaGetErrorString(es));
+        return DODRT_OK;
     }
     if (e == cudaSuccess && !frame->compact) {
         // pixels of tiles that belong to other ranks must read as "miss" / "not visible"
         e = cudaMemsetAsync(d_hits, 0xFF, slots * sizeof(dodrt_hit), st);
         if (e == cudaSuccess && num_lights) e = cudaMemsetAsync(d_vis, 0, slots * (size_t)num_lights, st);
     }
-    // Copies run on a second stream so that they hide behind kernels instead of following them:
+    // ---- staged (pageable host buffers).  Copies run on a second stream so that they hide behind kernels:
     //  * with shadow passes, the primary hit records (16 of the 17 B per pixel) go to the host WHILE the shadow
     //    kernels -- which only read them -- run; each light's visibility bytes follow their own pass;
     //  * a primary-only frame is traced in `bands` bands (whole tile rows for full-frame results, runs of local
     //    tiles for compact results, so a band's results are contiguous) and band k is copied while band k+1 is
     //    traced.  More bands cost ~0.2 ms each in launch/tail overhead (profiles/r01_e2e_bands.txt), hence 2.
-    std::vector<cudaEvent_t> events;
-    auto fence = [&](cudaStream_t from, cudaStream_t to) -> cudaError_t { // `to` waits for what `from` has queued
-        cudaEvent_t ev = nullptr;
-        cudaError_t err = cudaEventCreateWithFlags(&ev, cudaEventDisableTiming);
-        if (err != cudaSuccess) return err;
-        events.push_back(ev);
-        err = cudaEventRecord(ev, from);
-        return err == cudaSuccess ? cudaStreamWaitEvent(to, ev, 0) : err;
-    };
     if (e == cudaSuccess) {
         uint32_t tilesX, localTiles;
         frameTiles(frame, &tilesX, &localTiles);
@@ -977,7 +1330,7 @@ try {
                 hi = (uint64_t)((begin + count) / tilesX) * frame->tile_h * frame->width;
                 if (begin + count >= localTiles || hi > slots) hi = slots;
             }
-            e = fence(st, s->copyStream);
+            e = stagingFence(s, st, s->copyStream);
             if (e == cudaSuccess) {
                 e = cudaMemcpyAsync(hits + lo, d_hits + lo, (hi - lo) * sizeof(dodrt_hit), cudaMemcpyDeviceToHost, s->copyStream);
             }
@@ -986,21 +1339,17 @@ try {
             rc = launchFrame(s, kModeShadow, frame, d_tables, d_tables + frame->width, d_hits, lights + 3 * l,
                              d_vis + slots * l, st);
             if (rc != DODRT_OK) break;
-            e = fence(st, s->copyStream);
+            e = stagingFence(s, st, s->copyStream);
             if (e == cudaSuccess) {
                 e = cudaMemcpyAsync(visible + slots * l, d_vis + slots * l, slots, cudaMemcpyDeviceToHost, s->copyStream);
             }
         }
-        // the staging buffers are released on the compute stream: make it wait for the copies
-        if (e == cudaSuccess) e = fence(s->copyStream, st);
     }
-    if (e != cudaSuccess || rc != DODRT_OK) cudaStreamSynchronize(s->copyStream);
-    if (d_tables) cudaFreeAsync(d_tables, st);
-    if (d_hits) cudaFreeAsync(d_hits, st);
-    if (d_vis) cudaFreeAsync(d_vis, st);
+    // the staging buffers are re-used by the next call: both streams must have drained
+    cudaError_t ec = cudaStreamSynchronize(s->copyStream);
     cudaError_t es = cudaStreamSynchronize(st);
-    for (cudaEvent_t ev : events) cudaEventDestroy(ev);
     if (rc != DODRT_OK) return rc;
+    if (e == cudaSuccess) e = ec;
     if (e == cudaSuccess) e = es;
     if (e != cudaSuccess) return fail(DODRT_E_CUDA, "dodrt_trace_frame: %s", cudaGetErrorString(e));
     return DODRT_OK;
@@ -1050,6 +1399,146 @@ try {
     if (rc != DODRT_OK) return rc;
     if (e == cudaSuccess) e = es;
     if (e != cudaSuccess) return fail(DODRT_E_CUDA, "dodrt_trace_shadow: %s", cudaGetErrorString(e));
+    return DODRT_OK;
+}
+DODRT_CATCH
+
+// ---- several GPUs, one host process ------------------------------------------------------------------------------
+
+struct dodrt_multi {
+    std::vector<dodrt_scene *> scenes;
+    std::mutex mutex;
+    dodrt_frame_buffer *frameBuffer = nullptr;          // pageable host buffers: the frame assembles in scenes[0]'s HBM
+    std::vector<dodrt_frame_buffer *> views;            // per scene; views[0] == frameBuffer
+};
+
+static void multiDropFrameBuffer(dodrt_multi *m)
+{
+    for (size_t i = 1; i < m->views.size(); i++) dodrt_frame_buffer_destroy(m->views[i]);
+    m->views.clear();
+    dodrt_frame_buffer_destroy(m->frameBuffer);
+    m->frameBuffer = nullptr;
+}
+
+int dodrt_multi_create(dodrt_scene *const *scenes, uint32_t num_scenes, dodrt_multi **multi)
+try {
+    if (!scenes || !multi || num_scenes == 0) return fail(DODRT_E_INVALID, "NULL or empty scene list");
+    *multi = nullptr;
+    for (uint32_t i = 0; i < num_scenes; i++) {
+        if (!scenes[i]) return fail(DODRT_E_INVALID, "scenes[%u] is NULL", i);
+        for (uint32_t j = 0; j < i; j++) {
+            if (scenes[j]->device == scenes[i]->device) return fail(DODRT_E_INVALID, "scenes[%u] and scenes[%u] share device %d", j, i, scenes[i]->device);
+        }
+        int rc = ensureStream(scenes[i]);
+        if (rc != DODRT_OK) return rc;
+    }
+    std::unique_ptr<dodrt_multi> m(new dodrt_multi());
+    m->scenes.assign(scenes, scenes + num_scenes);
+    *multi = m.release();
+    return DODRT_OK;
+}
+DODRT_CATCH
+
+int dodrt_multi_destroy(dodrt_multi *m)
+try {
+    if (!m) return DODRT_OK;
+    multiDropFrameBuffer(m);
+    delete m;
+    return DODRT_OK;
+}
+DODRT_CATCH
+
+int dodrt_multi_trace_frame(dodrt_multi *m, const dodrt_frame *frame, const float *xs, const float *ys, const float *lights,
+                            uint32_t num_lights, dodrt_hit *hits, uint8_t *visible)
+try {
+    if (!m) return fail(DODRT_E_INVALID, "multi is NULL");
+    int rc = checkFrame(frame);
+    if (rc != DODRT_OK) return rc;
+    if (!xs || !ys || !hits) return fail(DODRT_E_INVALID, "NULL table/hit buffer");
+    if (num_lights && (!lights || !visible)) return fail(DODRT_E_INVALID, "NULL lights/visible buffer");
+    if (num_lights > (uint32_t)kMaxLights) return fail(DODRT_E_LIMIT, "%u lights exceed the limit of %d", num_lights, kMaxLights);
+    std::lock_guard<std::mutex> lock(m->mutex);
+    const uint32_t n = (uint32_t)m->scenes.size();
+    const uint64_t pixels = (uint64_t)frame->width * frame->height;
+    // where do the results go?  Pinned host buffers: straight from every GPU's kernel.  Otherwise via scenes[0]'s HBM.
+    void *mHits = nullptr, *mVis = nullptr;
+    {
+        DeviceGuard guard(m->scenes[0]->device);
+        mHits = mappedHostPointer(hits, pixels * sizeof(dodrt_hit));
+        mVis = num_lights ? mappedHostPointer(visible, pixels * num_lights) : nullptr;
+    }
+    const bool direct = mHits && (num_lights == 0 || mVis);
+    if (!direct) {
+        dodrt_frame_buffer *fb = m->frameBuffer;
+        if (!fb || fb->width != frame->width || fb->height != frame->height || fb->numLights < num_lights) {
+            multiDropFrameBuffer(m);
+            rc = dodrt_frame_buffer_create(m->scenes[0], frame->width, frame->height, num_lights, &m->frameBuffer);
+            if (rc != DODRT_OK) return rc;
+            m->views.assign(1, m->frameBuffer);
+            for (uint32_t i = 1; i < n; i++) {
+                dodrt_frame_buffer *v = nullptr;
+                rc = dodrt_frame_buffer_attach(m->scenes[i], m->frameBuffer, &v);
+                if (rc != DODRT_OK) {
+                    multiDropFrameBuffer(m);
+                    return rc;
+                }
+                m->views.push_back(v);
+            }
+        }
+    }
+    cudaError_t e = cudaSuccess;
+    uint32_t launched = 0;
+    for (uint32_t i = 0; i < n && rc == DODRT_OK && e == cudaSuccess; i++) { // asynchronous: all GPUs trace at the same time
+        dodrt_scene *s = m->scenes[i];
+        DeviceGuard guard(s->device);
+        if (!guard.ok) {
+            rc = fail(DODRT_E_CUDA, "cannot select device %d", s->device);
+            break;
+        }
+        s->hostMutex.lock();
+        launched = i + 1;
+        dodrt_frame f = *frame;
+        f.first_tile = i;
+        f.tile_stride = n;
+        f.compact = 1;
+        const uint64_t slots = frameSlots(&f);
+        if (slots == 0) continue;
+        const size_t tableFloats = (size_t)frame->width + frame->height;
+        e = growStaging(s->stTables, s->stTablesBytes, tableFloats * sizeof(float));
+        if (e == cudaSuccess) e = growStaging(s->stHits, s->stHitsBytes, slots * sizeof(dodrt_hit));
+        if (e == cudaSuccess) e = growStaging(s->stVis, s->stVisBytes, slots * (size_t)(num_lights ? num_lights : 1));
+        if (e == cudaSuccess) e = cudaMemcpyAsync(s->stTables, xs, frame->width * sizeof(float), cudaMemcpyHostToDevice, s->stream);
+        if (e == cudaSuccess) {
+            e = cudaMemcpyAsync(s->stTables + frame->width, ys, frame->height * sizeof(float), cudaMemcpyHostToDevice, s->stream);
+        }
+        if (e != cudaSuccess) break;
+        Mirror mir;
+        mir.byPixel = 1;
+        mir.lightStride = pixels;
+        if (direct) {
+            mir.hits = static_cast<dodrt_hit *>(mHits);
+            mir.visible = static_cast<uint8_t *>(mVis);
+        } else {
+            mir.hits = m->views[i]->hits();
+            mir.visible = m->views[i]->visible();
+        }
+        rc = traceFrameOnDevice(s, &f, s->stTables, s->stTables + frame->width, lights, num_lights, s->stHits, s->stVis, slots, &mir,
+                                s->stream);
+    }
+    for (uint32_t i = 0; i < launched; i++) {
+        dodrt_scene *s = m->scenes[i];
+        DeviceGuard guard(s->device);
+        cudaError_t es = cudaStreamSynchronize(s->stream);
+        if (e == cudaSuccess) e = es;
+        s->hostMutex.unlock();
+    }
+    if (rc != DODRT_OK) return rc;
+    if (e == cudaSuccess && !direct) {
+        DeviceGuard guard(m->scenes[0]->device);
+        e = cudaMemcpy(hits, m->frameBuffer->hits(), pixels * sizeof(dodrt_hit), cudaMemcpyDeviceToHost);
+        if (e == cudaSuccess && num_lights) e = cudaMemcpy(visible, m->frameBuffer->visible(), pixels * num_lights, cudaMemcpyDeviceToHost);
+    }
+    if (e != cudaSuccess) return fail(DODRT_E_CUDA, "dodrt_multi_trace_frame: %s", cudaGetErrorString(e));
     return DODRT_OK;
 }
 DODRT_CATCH

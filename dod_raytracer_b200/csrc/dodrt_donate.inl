@@ -22,23 +22,30 @@ enum FinishKind : uint32_t { kFinishRecord = 0, kFinishAnyRecord = 1, kFinishVis
 
 // What remains to be done with the kd-tree's answer for one ray (main.cpp:320-325 / 209-217 as the trace kernel
 // applies them): where the result goes and what it is when the tree finds nothing.
+constexpr uint64_t kNoMirror = ~0ull;
 struct Finish {
     uint64_t out;
+    uint64_t mirror; // index into the mirror buffers (TraceParams::mirror_*), kNoMirror = none
     uint32_t kind;
     float pre[4]; // kFinishRecord: the record before the tree (analytic hit or miss); kFinishAnyRecord: pre[0] = the ray's clip
 };
 
-__device__ __forceinline__ void finish_write(const TraceParams &p, uint32_t kind, uint64_t out, bool found, const Hit &hit,
-                                             const float pre[4])
+__device__ __forceinline__ void finish_write(const TraceParams &p, uint32_t kind, uint64_t out, uint64_t mirror, bool found,
+                                             const Hit &hit, const float pre[4])
 {
     if (kind == kFinishVisible) {
         p.visible[out] = found ? 0 : 1;
+        if (mirror != kNoMirror) {
+            p.mirror_visible[mirror] = found ? 0 : 1;
+        }
     } else if (kind == kFinishAnyRecord) {
         reinterpret_cast<float4 *>(p.hits)[out] = make_float4(pre[0], __uint_as_float(found ? 0u : DODRT_MISS), 0.0f, 0.0f);
-    } else if (found) {
-        reinterpret_cast<float4 *>(p.hits)[out] = make_float4(hit.t, __uint_as_float(hit.prim), hit.u, hit.v);
     } else {
-        reinterpret_cast<float4 *>(p.hits)[out] = make_float4(pre[0], pre[1], pre[2], pre[3]);
+        const float4 r = found ? make_float4(hit.t, __uint_as_float(hit.prim), hit.u, hit.v) : make_float4(pre[0], pre[1], pre[2], pre[3]);
+        reinterpret_cast<float4 *>(p.hits)[out] = r;
+        if (mirror != kNoMirror) {
+            reinterpret_cast<float4 *>(p.mirror_hits)[mirror] = r;
+        }
     }
 }
 
@@ -98,6 +105,8 @@ __device__ __noinline__ void donate_store(uint32_t *slots, uint32_t *ready, uint
     w[4] = r.w[4];
     w[5] = make_float4(r.w[5].x, r.w[5].y, __uint_as_float((uint32_t)fin->out), __uint_as_float((uint32_t)(fin->out >> 32)));
     uint32_t *stk = slots + (size_t)slot * kDonateSlotWords + 24;
+    stk[kDonateMirrorWord - 24] = (uint32_t)fin->mirror;
+    stk[kDonateMirrorWord - 24 + 1] = (uint32_t)(fin->mirror >> 32);
     for (int i = 0; i < r.sp; i++) {
         stk[3 * i + 0] = r.stackNode[i];
         stk[3 * i + 1] = __float_as_uint(r.stackTmin[i]);
@@ -178,6 +187,7 @@ __device__ __forceinline__ void resume_ray(const TraceParams &p, uint32_t slot)
     float stackTmin[kMaxStack];
     float stackTmax[kMaxStack];
     const uint32_t *stk = p.donate_slots + (size_t)slot * kDonateSlotWords + 24;
+    const uint64_t mirror = (uint64_t)__ldcg(stk + kDonateMirrorWord - 24) | ((uint64_t)__ldcg(stk + kDonateMirrorWord - 24 + 1) << 32);
     for (int i = 0; i < st.sp; i++) {
         stackNode[i] = __ldcg(stk + 3 * i);
         stackTmin[i] = __uint_as_float(__ldcg(stk + 3 * i + 1));
@@ -222,7 +232,7 @@ __device__ __forceinline__ void resume_ray(const TraceParams &p, uint32_t slot)
         }
     }
     if (lane == 0) {
-        finish_write(p, kind, out, found, hit, pre);
+        finish_write(p, kind, out, mirror, found, hit, pre);
     }
 }
 

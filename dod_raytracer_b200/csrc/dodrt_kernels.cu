@@ -334,7 +334,7 @@ __device__ __forceinline__ void leaf_step_coop(const DeviceScene &s, TreeState &
 template <bool SOA, bool SHARE, bool PACKED, bool DONATE, bool COMPACT = false>
 __device__ __forceinline__ bool kdtree_query_voted(const DeviceScene &s, bool enter, const float o[3], const float d[3],
                                                    bool any, float &clip, Hit &hit, const TraceParams *p = nullptr,
-                                                   const Finish *fin = nullptr, bool *donated = nullptr)
+                                                   const Finish *fin = nullptr, bool *donated = nullptr, bool allowDonate = true)
 {
     TreeState st;
     tree_enter(s, st, enter, o, d, clip);
@@ -386,7 +386,7 @@ __device__ __forceinline__ bool kdtree_query_voted(const DeviceScene &s, bool en
             break;
         }
         // do idle warps wait for rays?
-        const uint32_t want = p->donate_slots != nullptr ? donate_poll(*p) : 0u;
+        const uint32_t want = (p->donate_slots != nullptr && allowDonate) ? donate_poll(*p) : 0u;
         if (want != 0u) {
             donate_live_rays(*p, want, st, o, d, any, clip, hit, found, fin, stackNode, stackTmin, stackTmax, *donated);
         }
@@ -443,7 +443,8 @@ __device__ __forceinline__ bool analytic_chain(const DeviceScene &s, uint32_t cl
 template <int VARIANT>
 __device__ __forceinline__ bool query(const DeviceScene &s, uint32_t classes, bool valid, const float o[3],
                                       const float d[3], bool any, float clip, Hit &hit, const TraceParams *p = nullptr,
-                                      uint32_t kind = 0, uint64_t out = 0, bool *donated = nullptr)
+                                      uint32_t kind = 0, uint64_t out = 0, bool *donated = nullptr, uint64_t mirror = kNoMirror,
+                                      bool allowDonate = true)
 {
     bool found = false;
     const float clip0 = clip;
@@ -459,13 +460,14 @@ __device__ __forceinline__ bool query(const DeviceScene &s, uint32_t classes, bo
     if (VARIANT == kDonateVariant) {
         Finish fin;
         fin.out = out;
+        fin.mirror = mirror;
         fin.kind = kind;
         fin.pre[0] = kind == kFinishAnyRecord ? clip0 : hit.t;
         fin.pre[1] = __uint_as_float(hit.prim);
         fin.pre[2] = hit.u;
         fin.pre[3] = hit.v;
         h.t = clip, h.prim = DODRT_MISS, h.u = h.v = 0.0f;
-        if (kdtree_query_voted<true, false, false, true>(s, enter, o, d, any, clip, h, p, &fin, donated)) {
+        if (kdtree_query_voted<true, false, false, true>(s, enter, o, d, any, clip, h, p, &fin, donated, allowDonate)) {
             hit = h;
             found = true;
         }
@@ -640,6 +642,11 @@ __global__ void __launch_bounds__(128, VARIANT >= kDonateVariant ? 5 : DODRT_MIN
             uint64_t slot = 0;
             const bool inside = inRange && slot_to_pixel(p.frame, p.tiles_x, p.tile_order, item, col, row, slot);
             const uint64_t out = p.frame.compact ? slot : (uint64_t)row * p.frame.width + col;
+            // where the result goes in the mirror (a peer GPU's frame or pinned host memory), if there is one
+            // (a mirror with the local layout also receives the padded slots of edge tiles, like the local buffer)
+            const uint64_t mirrorIdx = inside ? (p.mirror_by_pixel ? (uint64_t)row * p.frame.width + col : out)
+                                              : ((inRange && p.frame.compact && !p.mirror_by_pixel) ? out : kNoMirror);
+            const uint64_t mirror = p.mirror_hits != nullptr ? mirrorIdx : kNoMirror;
             const float o[3] = {p.frame.origin[0], p.frame.origin[1], p.frame.origin[2]};
             float d[3] = {0.0f, 0.0f, 1.0f};
             if (inside) {
@@ -648,9 +655,13 @@ __global__ void __launch_bounds__(128, VARIANT >= kDonateVariant ? 5 : DODRT_MIN
             if (MODE == kModePrimary) {
                 Hit h;
                 bool donated = false;
-                query<VARIANT>(p.scene, p.classes, inside, o, d, false, kInfinity, h, &p, kFinishRecord, out, &donated);
+                query<VARIANT>(p.scene, p.classes, inside, o, d, false, kInfinity, h, &p, kFinishRecord, out, &donated, mirror);
                 if ((inside || (inRange && p.frame.compact)) && !donated) { // padded slots of edge tiles read as "miss"
-                    reinterpret_cast<float4 *>(p.hits)[out] = make_float4(h.t, __uint_as_float(h.prim), h.u, h.v);
+                    const float4 r = make_float4(h.t, __uint_as_float(h.prim), h.u, h.v);
+                    reinterpret_cast<float4 *>(p.hits)[out] = r;
+                    if (mirror != kNoMirror) {
+                        reinterpret_cast<float4 *>(p.mirror_hits)[mirror] = r;
+                    }
                 }
             } else {
                 bool shadowed = true, cast = false;
@@ -664,11 +675,15 @@ __global__ void __launch_bounds__(128, VARIANT >= kDonateVariant ? 5 : DODRT_MIN
                 }
                 Hit h;
                 bool donated = false;
+                const uint64_t vmirror = p.mirror_visible != nullptr ? mirrorIdx : kNoMirror;
                 const bool blocked = query<VARIANT>(p.scene, p.classes, cast, so, sd, true, sclip, h, &p, kFinishVisible, out,
-                                                    &donated);
+                                                    &donated, vmirror);
                 shadowed = !cast || blocked;
                 if ((inside || (inRange && p.frame.compact)) && !donated) {
                     p.visible[out] = shadowed ? 0 : 1;
+                    if (vmirror != kNoMirror) {
+                        p.mirror_visible[vmirror] = shadowed ? 0 : 1;
+                    }
                 }
             }
         }
@@ -693,6 +708,150 @@ __global__ void __launch_bounds__(128, VARIANT >= kDonateVariant ? 5 : DODRT_MIN
         atomicMax(p.counter + 27, t); // last helper gone
     }
 #endif
+}
+
+
+// ---- kModeFrame: primary + shadow rays of a frame share in ONE persistent launch ----------------------------------
+// Two work queues.  Queue 1 holds the primary batches (8x4 pixel blocks, tiles in heavy-first order); queue 2 holds the
+// shadow batches -- still a separate, coherent any-hit pass over 8x4 blocks (main.cpp:182-219 per pixel), but a tile's
+// shadow batches become claimable as soon as ITS primary records are complete instead of after the whole primary pass:
+//   * the warp that finishes the last primary batch of a tile (tile_done[t] reaches batches-per-tile) appends the tile to
+//     ready_queue;
+//   * shadow batch number q belongs to the (q / (batches-per-tile * lights))-th tile of ready_queue; a warp that claims a
+//     batch whose tile is not published yet waits for it (the tile's primary batches are in flight on resident warps).
+// The tail of the primary queue (its slowest batches) therefore overlaps shadow work, and the pass has ONE ramp and ONE
+// tail instead of two of each with a grid-wide barrier in between -- which is what limited an 8-way split of a 4K frame
+// (0.26 + 0.53 ms per rank against 0.47 ms ideal).  Per pixel nothing changes: same primary query, same shadow ray from
+// the same hit record (read back from memory, like the separate pass does), same any-hit query.
+// Donation (VARIANT 7): only shadow rays are ever suspended.  A helper exists once the shadow queue is exhausted, and the
+// last shadow claims wait for the last tiles, whose primary batches may still run: those must not give rays away (a
+// tile would be published while a record is still pending), hence allowDonate = false in queue 1.
+template <int VARIANT>
+__global__ void __launch_bounds__(128, VARIANT >= kDonateVariant ? 5 : DODRT_MINBLOCKS) trace_frame_kernel(const TraceParams p)
+{
+    const uint32_t lane = threadIdx.x & 31u;
+    if (VARIANT == kDonateVariant && p.donate_slots != nullptr && lane == 0) {
+        atomicAdd(p.counter + kDonateStarted, 1ull); // see donate_helper_loop
+    }
+    const dodrt_frame &f = p.frame;
+    const uint32_t tilePixels = f.tile_w * f.tile_h;
+    const uint32_t bpt = tilePixels >> 5; // batches per tile
+    const uint32_t bpr = f.tile_w >> 3;   // 8x4 blocks per tile row
+    const uint32_t perTile = bpt * p.num_lights;
+    const float o[3] = {f.origin[0], f.origin[1], f.origin[2]};
+    bool primaryLeft = true;
+    // ONE loop and one call site of the query for both queues (half the code of two specialised loops: the hot
+    // traversal is the same, only the ray set-up and the result differ)
+    for (;;) {
+        unsigned long long base = 0;
+        if (primaryLeft) {
+            if (lane == 0) {
+                base = atomicAdd(p.counter, 32ull);
+            }
+            base = __shfl_sync(0xffffffffu, base, 0);
+            primaryLeft = base < p.count;
+        }
+        if (!primaryLeft) {
+            if (lane == 0) {
+                base = atomicAdd(p.counter + kShadowNext, 32ull);
+            }
+            base = __shfl_sync(0xffffffffu, base, 0);
+            if (base >= p.shadow_count) {
+                break;
+            }
+        }
+        const bool shadow = !primaryLeft;
+        uint32_t col = 0, row = 0, localTile = 0, light = 0;
+        uint64_t slot = 0;
+        bool inside;
+        if (!shadow) { // ---- queue 1: a primary batch
+            inside = slot_to_pixel(f, p.tiles_x, p.tile_order, base + lane, col, row, slot);
+            localTile = (uint32_t)(slot / tilePixels);
+        } else { // ---- queue 2: a shadow batch of a complete tile, one light after the other per tile
+            const uint64_t seq = base >> 5;
+            const uint32_t readyIdx = (uint32_t)(seq / perTile);
+            const uint32_t rem = (uint32_t)(seq - (uint64_t)readyIdx * perTile);
+            light = rem / bpt;
+            const uint32_t block = rem - light * bpt;
+            if (lane == 0) {
+                unsigned ns = 100;
+                while ((localTile = *reinterpret_cast<const volatile uint32_t *>(p.ready_queue + readyIdx)) == 0u) {
+                    __nanosleep(ns);
+                    ns = ns < 1600u ? ns * 2u : ns;
+                }
+            }
+            localTile = __shfl_sync(0xffffffffu, localTile, 0) - 1u;
+            __threadfence(); // acquire side of the tile's publication
+            const uint32_t tile = f.first_tile + localTile * f.tile_stride;
+            const uint32_t tx = tile % p.tiles_x, ty = tile / p.tiles_x;
+            const uint32_t bx = block % bpr, by = block / bpr;
+            col = tx * f.tile_w + bx * 8 + (lane & 7u);
+            row = ty * f.tile_h + by * 4 + (lane >> 3);
+            inside = col < f.width && row < f.height;
+            slot = (uint64_t)localTile * tilePixels + block * 32u + lane;
+        }
+        const uint64_t pixel = (uint64_t)row * f.width + col;
+        const uint64_t idx = f.compact ? slot : pixel;
+        const uint64_t midx = p.mirror_by_pixel ? pixel : idx;
+        float rd[3] = {0.0f, 0.0f, 1.0f}, ro[3] = {o[0], o[1], o[2]};
+        float clip = kInfinity;
+        bool cast = inside;
+        // (a mirror with the local layout also receives the padded slots of edge tiles, like the local buffer)
+        const bool mirrored = inside || (f.compact && !p.mirror_by_pixel);
+        uint64_t out = idx, mirror = (p.mirror_hits != nullptr && mirrored) ? midx : kNoMirror;
+        if (inside) {
+            primary_dir(__ldg(p.xs + col), __ldg(p.ys + row), rd);
+        }
+        if (shadow) {
+            out = (uint64_t)light * p.visible_light_stride + idx;
+            mirror = (p.mirror_visible != nullptr && mirrored) ? (uint64_t)light * p.mirror_light_stride + midx : kNoMirror;
+            cast = false;
+            clip = 0.0f;
+            if (inside) {
+                const float4 ph = __ldcg(reinterpret_cast<const float4 *>(p.hits) + idx); // written in this launch: L2, not L1
+                if (__float_as_uint(ph.y) != DODRT_MISS) {
+                    const float light3[3] = {p.lights[light][0], p.lights[light][1], p.lights[light][2]};
+                    float so[3], sd[3];
+                    shadow_ray(o, rd, ph.x, light3, so, sd, clip);
+                    ro[0] = so[0], ro[1] = so[1], ro[2] = so[2];
+                    rd[0] = sd[0], rd[1] = sd[1], rd[2] = sd[2];
+                    cast = true;
+                }
+            }
+        }
+        Hit h;
+        bool donated = false;
+        const bool found = query<VARIANT>(p.scene, p.classes, cast, ro, rd, shadow, clip, h, &p, shadow ? kFinishVisible : kFinishRecord,
+                                          out, &donated, mirror, shadow);
+        if ((inside || f.compact) && !donated) { // padded slots of edge tiles read as "miss" / "not visible"
+            if (shadow) {
+                const uint8_t v = (cast && !found) ? 1 : 0;
+                p.visible[out] = v;
+                if (mirror != kNoMirror) {
+                    p.mirror_visible[mirror] = v;
+                }
+            } else {
+                const float4 r = make_float4(h.t, __uint_as_float(h.prim), h.u, h.v);
+                reinterpret_cast<float4 *>(p.hits)[out] = r;
+                if (mirror != kNoMirror) {
+                    reinterpret_cast<float4 *>(p.mirror_hits)[mirror] = r;
+                }
+            }
+        }
+        if (!shadow && p.shadow_count != 0) {
+            // publish: every lane's record must be visible before the tile can be counted complete
+            __threadfence();
+            __syncwarp();
+            if (lane == 0 && atomicAdd(p.tile_done + localTile, 1u) + 1u == bpt) {
+                __threadfence(); // the other batches' records (released by their atomicAdd) before the publication
+                const unsigned long long k = atomicAdd(p.counter + kReadyTail, 1ull);
+                *reinterpret_cast<volatile uint32_t *>(p.ready_queue + k) = localTile + 1u;
+            }
+        }
+    }
+    if (VARIANT == kDonateVariant && p.donate_slots != nullptr) {
+        donate_helper_loop(p);
+    }
 }
 
 #include "dodrt_pool_kernel.inl"
@@ -784,7 +943,9 @@ template <int MODE, int VARIANT> cudaError_t config_for(int device, LaunchConfig
     int sms = 0, perSm = 0;
     cudaError_t e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
     if (e != cudaSuccess) return e;
-    if constexpr (VARIANT == 4 && MODE != kModeShadowRays) {
+    if constexpr (MODE == kModeFrame) { // the fused kernel exists as the plain voted kernel and as the donating one
+        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, trace_frame_kernel<(VARIANT == kDonateVariant ? kDonateVariant : 3)>, 128, 0);
+    } else if constexpr (VARIANT == 4 && MODE != kModeShadowRays) {
         e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, trace_kernel_pool<MODE>, 128, 0);
     } else if constexpr (VARIANT == 4) { // the pool kernel has no explicit-ray shadow mode: variant 3 serves it
         e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, trace_kernel<MODE, 3>, 128, 0);
@@ -800,7 +961,9 @@ template <int MODE, int VARIANT> cudaError_t config_for(int device, LaunchConfig
 
 template <int MODE, int VARIANT> void launch_one(const TraceParams &p, const LaunchConfig &cfg, cudaStream_t stream)
 {
-    if constexpr (VARIANT == 4 && MODE != kModeShadowRays) {
+    if constexpr (MODE == kModeFrame) {
+        trace_frame_kernel<(VARIANT == kDonateVariant ? kDonateVariant : 3)><<<cfg.grid, cfg.block, 0, stream>>>(p);
+    } else if constexpr (VARIANT == 4 && MODE != kModeShadowRays) {
         trace_kernel_pool<MODE><<<cfg.grid, cfg.block, 0, stream>>>(p);
     } else if constexpr (VARIANT == 4) {
         trace_kernel<MODE, 3><<<cfg.grid, cfg.block, 0, stream>>>(p);
@@ -815,6 +978,7 @@ template <int VARIANT> cudaError_t config_mode(int device, TraceMode mode, Launc
     case kModeRays: return config_for<kModeRays, VARIANT>(device, cfg);
     case kModePrimary: return config_for<kModePrimary, VARIANT>(device, cfg);
     case kModeShadow: return config_for<kModeShadow, VARIANT>(device, cfg);
+    case kModeFrame: return config_for<kModeFrame, VARIANT>(device, cfg);
     default: return config_for<kModeShadowRays, VARIANT>(device, cfg);
     }
 }
@@ -825,6 +989,7 @@ template <int VARIANT> void launch_mode(TraceMode mode, const TraceParams &p, co
     case kModeRays: launch_one<kModeRays, VARIANT>(p, cfg, stream); break;
     case kModePrimary: launch_one<kModePrimary, VARIANT>(p, cfg, stream); break;
     case kModeShadow: launch_one<kModeShadow, VARIANT>(p, cfg, stream); break;
+    case kModeFrame: launch_one<kModeFrame, VARIANT>(p, cfg, stream); break;
     default: launch_one<kModeShadowRays, VARIANT>(p, cfg, stream); break;
     }
 }
@@ -887,7 +1052,10 @@ cudaError_t launch_trace(TraceMode mode, const TraceParams &params, const Launch
                          cudaMemPool_t pool, void *persistentQueue, uint32_t epoch)
 {
     TraceParams p = params;
-    cudaError_t e = cudaMemsetAsync(p.counter, 0, sizeof(unsigned long long) * kCounterWords, stream);
+    cudaError_t e = cudaSuccess;
+    if (mode != kModeFrame) { // kModeFrame: the caller zeroes counters + tile bookkeeping with one memset
+        e = cudaMemsetAsync(p.counter, 0, sizeof(unsigned long long) * kCounterWords, stream);
+    }
     if (e != cudaSuccess) return e;
 #ifdef DODRT_TIMELINE
     cudaMemsetAsync(p.counter + 24, 0xFF, 16, stream); // the two minima
@@ -917,9 +1085,9 @@ cudaError_t launch_trace(TraceMode mode, const TraceParams &params, const Launch
         p.donate_slots = reinterpret_cast<uint32_t *>(static_cast<char *>(mem) + readyBytes);
         p.donate_capacity = (uint32_t)cap;
     }
-    if (p.tile_order && (mode == kModePrimary || mode == kModeShadow)) {
+    if (p.tile_order && (mode == kModePrimary || mode == kModeShadow || mode == kModeFrame)) {
         const unsigned blocks = (p.num_local_tiles + 127u) / 128u;
-        if (mode == kModePrimary) {
+        if (mode != kModeShadow) {
             order_tiles_kernel<kModePrimary><<<blocks, 128, 0, stream>>>(p);
         } else {
             order_tiles_kernel<kModeShadow><<<blocks, 128, 0, stream>>>(p);

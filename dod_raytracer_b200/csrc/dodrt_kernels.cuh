@@ -9,8 +9,9 @@ enum TraceMode : int {
     kModePrimary = 1, // in-kernel primary ray generation     (dodrt_trace_primary*)
     kModeShadow = 2,  // in-kernel shadow ray generation      (dodrt_trace_shadow*)
     kModeShadowRays = 3, // shadow rays from an explicit ray batch + its hits (bounce loop of dodrt_render*)
+    kModeFrame = 4,   // primary + shadow batches of a frame share in ONE launch (trace_frame_kernel, dodrt_trace_frame_device)
 };
-constexpr int kNumModes = 4;
+constexpr int kNumModes = 5;
 
 constexpr int kNumVariants = 9;    // see the header comment of dodrt_kernels.cu
 constexpr int kDefaultVariant = 3;
@@ -46,16 +47,37 @@ struct TraceParams {
     uint32_t *donate_ready;   // donate_capacity words; slot i is filled when donate_ready[i] == donate_epoch
     uint32_t donate_epoch;    // non-zero, unique per launch on a persistent queue (stale words of earlier launches never match)
     uint32_t donate_capacity;
+    // Frame modes: optional MIRROR of the results, written by the kernels themselves next to the local copy while they
+    // run -- a peer GPU's frame over NVLink (image-tile split: every rank fills rank 0's row-major frame directly, no
+    // gather, no assembly pass) or pinned host memory (the caller's buffers: no D2H copy after the kernel).  Indexed by
+    // pixel (row * width + col) when mirror_by_pixel, else like the local buffers.  Visibility of light l at
+    // mirror_visible[l * mirror_light_stride + index].
+    dodrt_hit *mirror_hits;
+    uint8_t *mirror_visible;
+    uint64_t mirror_light_stride;
+    uint32_t mirror_by_pixel;
+    // kModeFrame: the lights of the shadow queue, visible[l * visible_light_stride + slot]; per-tile bookkeeping that
+    // makes a tile's shadow batches claimable once its primary records are complete (all zeroed before the launch):
+    // tile_done[t] = primary batches of local tile t finished; ready_queue[k] = 1 + the k-th tile that became complete
+    uint32_t num_lights;
+    float lights[16][3];
+    uint64_t visible_light_stride;
+    uint64_t shadow_count; // count * num_lights
+    uint32_t *tile_done;
+    uint32_t *ready_queue;
 };
 
 // counters (one 256-B block per launch): [0] next work item, [1]/[2] heavy/light tiles placed (order_tiles_kernel);
+// kModeFrame: [3] next shadow item, [4] tiles published in ready_queue;
 // on their own 128-B line, away from the work counter every warp hammers: [16] warps that left the main loop,
 // [17] donation tickets taken by helpers, [18] donation slots reserved by donors, [19] warps that entered the kernel
 // (dodrt_donate.inl)
 constexpr int kCounterWords = 32;
+constexpr int kShadowNext = 3, kReadyTail = 4;
 constexpr int kDonateFinished = 16, kDonateHead = 17, kDonateTail = 18, kDonateStarted = 19;
 constexpr int kDonateVariant = 7;
-constexpr int kDonateSlotWords = 80; // 24 header words + 16 stack entries x 3 + 8 spare = 320 B
+constexpr int kDonateSlotWords = 80; // 24 header words + 16 stack entries x 3 + mirror index (2) + 6 spare = 320 B
+constexpr int kDonateMirrorWord = 72;
 constexpr int kDonateMaxStack = 16;
 constexpr uint64_t kDonateBelowBatches = 64; // auto: donate when a pass has fewer 32-ray batches per warp than this
 

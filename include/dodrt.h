@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define DODRT_ABI_VERSION 1
+#define DODRT_ABI_VERSION 2
 
 #if defined(__GNUC__)
 #define DODRT_API __attribute__((visibility("default")))
@@ -207,7 +207,60 @@ DODRT_API int dodrt_trace_primary_device(dodrt_scene *scene, const dodrt_frame *
 DODRT_API int dodrt_trace_shadow_device(dodrt_scene *scene, const dodrt_frame *frame, const float *d_xs, const float *d_ys,
                               const dodrt_hit *d_hits, const float light[3], uint8_t *d_visible, void *stream);
 
-/* Multi-GPU frame assembly.  After an image-tile split over N ranks (frame->tile_stride = N, rank r traced
+/* ---- one launch per frame share, results written where they are needed ------------------------------
+ * dodrt_trace_frame_device = primary rays + one canSeeLight query per light and hit pixel (rayTrace at k = 0,
+ * main.cpp:297-334 without the shading) for this call's tiles, as ONE persistent kernel with two work queues: a
+ * tile's shadow batches (still a separate, coherent pass over 8x4 pixel blocks) become claimable as soon as that
+ * tile's primary hit records are complete, so the tail of the primary queue overlaps shadow work.  d_hits /
+ * d_visible ([num_lights][slots]) are laid out as frame->compact says; lights is a HOST array of num_lights x 3.
+ * `mirror` (optional): a frame buffer view for this scene's GPU (dodrt_frame_buffer_*); every result is ALSO written
+ * into that row-major frame by the kernel itself -- with an image-tile split every rank passes a view of rank 0's
+ * frame buffer and the frame assembles itself over NVLink while it is traced: no gather, no assembly pass.
+ * Replaces the reference's own split of the frame over its threads (main.cpp:371-394) + the shared image buffer. */
+typedef struct dodrt_frame_buffer dodrt_frame_buffer; /* opaque */
+DODRT_API int dodrt_trace_frame_device(dodrt_scene *scene, const dodrt_frame *frame, const float *d_xs, const float *d_ys,
+                                       const float *lights, uint32_t num_lights, dodrt_hit *d_hits, uint8_t *d_visible,
+                                       dodrt_frame_buffer *mirror, void *stream);
+
+/* A row-major frame -- hit records [height*width], then visibility [num_lights][height*width] -- in the HBM of
+ * `owner`'s GPU that kernels running on OTHER GPUs write into directly (NVLink / NVSwitch peer stores): the analogue of
+ * the one `imageData` block all of the reference's threads write (main.cpp:369,336-340).
+ *   same process : dodrt_frame_buffer_attach(scene_on_other_gpu, fb, &view)   (enables peer access)
+ *   other process: dodrt_frame_buffer_export(fb, &desc) -> ship the 96-byte descriptor (MPI, torch.distributed, a pipe)
+ *                  -> dodrt_frame_buffer_open(scene_on_other_gpu, &desc, &view)   (CUDA IPC, same node)
+ * The owner passes `fb` itself as its own mirror.  Initial contents: DODRT_MISS / 0.  Destroy views before the owner's
+ * buffer; a buffer outlives neither its owner's process nor (for views) the scene it was opened for. */
+typedef struct dodrt_frame_buffer_desc {
+    uint32_t width, height, num_lights, device;
+    uint64_t bytes;
+    uint8_t ipc_handle[64];
+    uint8_t reserved[8];
+} dodrt_frame_buffer_desc;
+DODRT_API int dodrt_frame_buffer_create(dodrt_scene *owner, uint32_t width, uint32_t height, uint32_t num_lights,
+                                        dodrt_frame_buffer **fb);
+DODRT_API int dodrt_frame_buffer_export(dodrt_frame_buffer *fb, dodrt_frame_buffer_desc *desc);
+DODRT_API int dodrt_frame_buffer_open(dodrt_scene *user, const dodrt_frame_buffer_desc *desc, dodrt_frame_buffer **view);
+DODRT_API int dodrt_frame_buffer_attach(dodrt_scene *user, dodrt_frame_buffer *owner_fb, dodrt_frame_buffer **view);
+DODRT_API int dodrt_frame_buffer_pointers(dodrt_frame_buffer *fb, dodrt_hit **d_hits, uint8_t **d_visible);
+DODRT_API int dodrt_frame_buffer_destroy(dodrt_frame_buffer *fb);
+
+/* ---- several GPUs, one host process ---------------------------------------------------------------------------
+ * The reference renders one frame with all the threads of its process (main.cpp:371-394: one row band per core);
+ * dodrt_multi renders one frame with all the GPUs of the process: scene replicated (one populated dodrt_scene per GPU,
+ * created and filled by the caller with the same arrays), image tiles dealt round-robin over the GPUs, and ONE frame
+ * buffer in host memory that every GPU fills in place.  frame describes the whole frame (first_tile / tile_stride /
+ * compact are ignored); hits is [height*width], visible [num_lights][height*width], both row-major.  With pinned
+ * host buffers (cudaHostAlloc / cudaHostRegister) every GPU's kernel stores its tiles straight into them over its own
+ * PCIe link while it traces; with pageable buffers the GPUs assemble the frame in scenes[0]'s HBM over NVLink first and
+ * one copy brings it to the host.  Calls on one dodrt_multi are serialised. */
+typedef struct dodrt_multi dodrt_multi; /* opaque */
+DODRT_API int dodrt_multi_create(dodrt_scene *const *scenes, uint32_t num_scenes, dodrt_multi **multi);
+DODRT_API int dodrt_multi_trace_frame(dodrt_multi *multi, const dodrt_frame *frame, const float *xs, const float *ys,
+                                      const float *lights, uint32_t num_lights, dodrt_hit *hits, uint8_t *visible);
+DODRT_API int dodrt_multi_destroy(dodrt_multi *multi);
+
+/* Multi-GPU frame assembly (kept for callers that gather compact blocks themselves, e.g. with NCCL; the frame buffer
+ * mirror above makes it unnecessary).  After an image-tile split over N ranks (frame->tile_stride = N, rank r traced
  * with first_tile = r, compact = 1) and a gather that places rank r's compact results at
  * d_compact_*[r * slots_per_rank ...], this writes the row-major full frame: hits_out[row*width+col] and,
  * when both visibility pointers are non-NULL, visible_out[row*width+col].  frame->first_tile is ignored. */

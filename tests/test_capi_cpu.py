@@ -24,7 +24,8 @@ def test_library_exports_every_declared_symbol():
     assert sorted(capi.EXPORTED_SYMBOLS) == names
     for n in names:
         assert getattr(lib, n) is not None
-    assert lib.dodrt_abi_version() == 1
+    assert lib.dodrt_abi_version() == capi.ABI_VERSION == 2
+    assert C.sizeof(capi.FrameBufferDesc) == 96
 
 
 def test_struct_layouts_match_header():

@@ -1,0 +1,201 @@
+"""GPU (-m gpu): the one-launch frame path (trace_frame_kernel: primary + shadow queues with per-tile readiness),
+result mirrors (a peer GPU's frame buffer, pinned host memory), frame buffers shared between processes (CUDA IPC) and
+the several-GPUs-one-process API.  Everything must reproduce the bytes of the separate primary / shadow passes, which
+tests/test_gpu_parity.py pins to the oracle, the reference fixtures and the reference itself."""
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+from dod_raytracer_b200 import capi, host
+from gpu_util import upload
+from oracle_api import CLS_CYLINDER, CLS_PLANE, CLS_SPHERE, CLS_TREE, MISS
+from scenes import GOLDEN, LIGHT0, teapot_scene
+
+pytestmark = pytest.mark.gpu
+ALL = CLS_SPHERE | CLS_PLANE | CLS_CYLINDER | CLS_TREE
+LIGHTS2 = np.stack([LIGHT0, np.array([4.0, 4.3, 3.3], np.float32)])  # lights[0], lights[1] of main.cpp:284-285
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _device_frame(g, frame, xs, ys, lights, mirror=None, fused=True):
+    """dodrt_trace_frame_device on torch buffers -> (hits, vis[lights, slots]) as numpy"""
+    import torch
+    dev = torch.device("cuda", g.device)
+    with torch.cuda.device(dev):
+        d_xs, d_ys = torch.from_numpy(xs).to(dev), torch.from_numpy(ys).to(dev)
+        slots = capi.frame_local_pixels(frame) if frame.compact else frame.width * frame.height
+        d_hits = torch.full((slots, 16), 0xAB, dtype=torch.uint8, device=dev)
+        d_vis = torch.full((len(lights), slots), 0xCD, dtype=torch.uint8, device=dev)
+        os.environ["DODRT_FUSED"] = "1" if fused else "0"
+        try:
+            g.trace_frame_device(frame, d_xs.data_ptr(), d_ys.data_ptr(), lights, d_hits.data_ptr(), d_vis.data_ptr(), mirror,
+                                 torch.cuda.current_stream().cuda_stream)
+        finally:
+            os.environ.pop("DODRT_FUSED", None)
+        torch.cuda.synchronize(dev)
+        return d_hits.cpu().numpy().reshape(-1).view(capi.HIT_DT), d_vis.cpu().numpy()
+
+
+class _RawDeviceBytes:
+    """a device address as something torch.as_tensor understands"""
+
+    def __init__(self, ptr, nbytes):
+        self.__cuda_array_interface__ = {"shape": (nbytes,), "typestr": "|u1", "data": (ptr, False), "version": 2}
+
+
+def _read_frame_buffer(fb, w, h, nl, device=0):
+    import torch
+    hp, vp = fb.pointers()
+    with torch.cuda.device(device):
+        torch.cuda.synchronize()
+        hits = torch.as_tensor(_RawDeviceBytes(hp, w * h * 16), device=f"cuda:{device}").cpu().numpy().view(capi.HIT_DT).copy()
+        vis = (torch.as_tensor(_RawDeviceBytes(vp, nl * w * h), device=f"cuda:{device}").cpu().numpy().reshape(nl, w * h).copy()
+               if nl else np.zeros((0, w * h), np.uint8))
+    return hits, vis
+
+
+@pytest.fixture(scope="module", params=[-1, 3, 7, 0], ids=lambda v: f"variant{v}")
+def teapot(request):
+    """auto / plain fused / donating fused / a variant without a fused form (falls back to separate passes)"""
+    g = upload(teapot_scene(full=True))
+    g.set_kernel_variant(request.param)
+    yield g
+    g.close()
+
+
+@pytest.mark.parametrize("w,h,tile", [(640, 360, (32, 32)), (500, 277, (16, 8)), (1920, 1080, (32, 32))])
+def test_fused_launch_equals_separate_passes(teapot, w, h, tile):
+    g = teapot
+    xs, ys = host.ray_tables(w, h)
+    frame = capi.Frame.make(w, h, classes=ALL, tile=tile)
+    want_h, want_v = _device_frame(g, frame, xs, ys, LIGHTS2, fused=False)
+    before = g.launch_count()
+    got_h, got_v = _device_frame(g, frame, xs, ys, LIGHTS2, fused=True)
+    assert got_h.tobytes() == want_h.tobytes() and got_v.tobytes() == want_v.tobytes()
+    assert g.launch_count() - before <= 3  # one frame kernel (+ the tile-order helper), not 1 + lights passes
+    assert want_v[0].sum() > 0 and want_v[1].tobytes() != want_v[0].tobytes()
+    # primary only (no shadow queue)
+    got_h0, _ = _device_frame(g, frame, xs, ys, LIGHTS2[:0])
+    assert got_h0.tobytes() == want_h.tobytes()
+
+
+def test_fused_tile_split_with_frame_buffer_mirror(teapot):
+    """every rank of an image-tile split writes its pixels straight into ONE row-major frame buffer (here all ranks
+    run one after the other on the same GPU; tests/test_gpu_multi.py does it across GPUs and processes)"""
+    g = teapot
+    w, h = 500, 277
+    xs, ys = host.ray_tables(w, h)
+    full_h, full_v = _device_frame(g, capi.Frame.make(w, h, classes=ALL), xs, ys, LIGHTS2, fused=False)
+    for world, tile in ((2, (32, 32)), (5, (16, 8))):
+        with capi.FrameBuffer.create(g, w, h, 2) as fb:
+            hits0, vis0 = _read_frame_buffer(fb, w, h, 2)
+            assert (hits0["prim"] == MISS).all() and not vis0.any()
+            for rank in range(world):
+                f = capi.Frame.make(w, h, classes=ALL, tile=tile, first_tile=rank, tile_stride=world, compact=1)
+                m = capi.frame_pixel_map(f)
+                ok = m != 0xFFFFFFFF
+                lh, lv = _device_frame(g, f, xs, ys, LIGHTS2, mirror=fb)
+                assert lh[ok].tobytes() == full_h[m[ok]].tobytes() and (lh["prim"][~ok] == MISS).all()
+                assert lv[:, ok].tobytes() == full_v[:, m[ok]].tobytes() and not lv[:, ~ok].any()
+            hits, vis = _read_frame_buffer(fb, w, h, 2)
+            assert hits.tobytes() == full_h.tobytes() and vis.tobytes() == full_v.tobytes()
+    with capi.FrameBuffer.create(g, w, h, 1) as small:  # a mirror with fewer lights than the call is refused
+        with pytest.raises(capi.DodrtError):
+            _device_frame(g, capi.Frame.make(w, h, classes=ALL), xs, ys, LIGHTS2, mirror=small)
+
+
+def test_host_buffers_zero_copy_equals_staged(teapot, monkeypatch):
+    """dodrt_trace_frame with PINNED host buffers lets the kernel store the results into them (no D2H copies);
+    pageable buffers are staged.  Same bytes, full-frame and compact (padded slots included)."""
+    import torch
+    g = teapot
+    w, h = 1000, 562
+    xs, ys = host.ray_tables(w, h)
+    for kw in (dict(), dict(first_tile=1, tile_stride=3, compact=1)):
+        frame = capi.Frame.make(w, h, classes=ALL, **kw)
+        slots = capi.frame_local_pixels(frame) if frame.compact else w * h
+        monkeypatch.setenv("DODRT_ZEROCOPY", "0")
+        want_h, want_v = g.trace_frame(frame, xs, ys, LIGHTS2)
+        monkeypatch.delenv("DODRT_ZEROCOPY")
+        ph = torch.full((slots, 16), 0x5A, dtype=torch.uint8).pin_memory().numpy().reshape(-1).view(capi.HIT_DT)
+        pv = torch.full((2, slots), 0x5A, dtype=torch.uint8).pin_memory().numpy()
+        before = g.launch_count()
+        g.trace_frame(frame, xs, ys, LIGHTS2, ph, pv)
+        assert ph.tobytes() == want_h.tobytes() and pv.tobytes() == want_v.tobytes()
+        # primary only into pinned memory
+        ph[:] = np.zeros(1, capi.HIT_DT)
+        g.trace_frame(frame, xs, ys, LIGHTS2[:0], ph, None)
+        assert ph.tobytes() == want_h.tobytes()
+        assert g.launch_count() > before
+
+
+def test_frame_buffer_shared_with_another_process(tmp_path):
+    """CUDA IPC: a second PROCESS opens the exported descriptor and its kernels fill the owner's frame buffer
+    (what every rank >= 1 of bench.py does with rank 0's frame)."""
+    w, h = 480, 270
+    scene = teapot_scene(full=True)
+    xs, ys = host.ray_tables(w, h)
+    with upload(scene) as g:
+        full_h, full_v = _device_frame(g, capi.Frame.make(w, h, classes=ALL), xs, ys, LIGHT0[None, :], fused=False)
+        with capi.FrameBuffer.create(g, w, h, 1) as fb:
+            desc = tmp_path / "desc.bin"
+            desc.write_bytes(fb.export().to_bytes())
+            f0 = capi.Frame.make(w, h, classes=ALL, first_tile=0, tile_stride=2, compact=1)
+            _device_frame(g, f0, xs, ys, LIGHT0[None, :], mirror=fb)  # rank 0 = this process
+            env = dict(os.environ, PYTHONPATH=os.pathsep.join([ROOT, os.path.join(ROOT, "tests")]))
+            r = subprocess.run([sys.executable, os.path.join(ROOT, "tests", "tools", "ipc_peer.py"), str(desc), "1", "2"],
+                               env=env, capture_output=True, text=True, timeout=300)
+            assert r.returncode == 0, r.stdout + r.stderr
+            hits, vis = _read_frame_buffer(fb, w, h, 1)
+            assert hits.tobytes() == full_h.tobytes() and vis.tobytes() == full_v.tobytes()
+
+
+def test_multi_with_one_gpu_and_with_all_gpus():
+    """dodrt_multi: N GPUs of this process fill ONE host frame (pinned: straight from the kernels; pageable: assembled
+    in scenes[0]'s HBM over peer stores first).  Runs with however many GPUs the box has (1 is a valid group)."""
+    import torch
+    w, h = 1000, 562
+    scene = teapot_scene(full=True)
+    xs, ys = host.ray_tables(w, h)
+    frame = capi.Frame.make(w, h, classes=ALL)
+    with upload(scene) as g:
+        want_h, want_v = _device_frame(g, frame, xs, ys, LIGHTS2, fused=False)
+    ngpu = capi.device_count()
+    for n in sorted({1, ngpu}):
+        scenes = [upload(scene, d) for d in range(n)]
+        try:
+            with capi.Multi(scenes) as m:
+                hits, vis = m.trace_frame(frame, xs, ys, LIGHTS2)  # pageable
+                assert hits.tobytes() == want_h.tobytes() and vis.tobytes() == want_v.tobytes(), f"{n} GPUs pageable"
+                ph = torch.zeros((w * h, 16), dtype=torch.uint8).pin_memory().numpy().reshape(-1).view(capi.HIT_DT)
+                pv = torch.zeros((2, w * h), dtype=torch.uint8).pin_memory().numpy()
+                for _ in range(2):
+                    m.trace_frame(frame, xs, ys, LIGHTS2, ph, pv)
+                assert ph.tobytes() == want_h.tobytes() and pv.tobytes() == want_v.tobytes(), f"{n} GPUs pinned"
+        finally:
+            for s in scenes:
+                s.close()
+
+
+def test_scene_on_another_device_than_the_current_one():
+    """streams / pools must be created on the scene's device, not on the caller's current one."""
+    import torch
+    if capi.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    scene = teapot_scene(full=True)
+    w, h = 320, 180
+    xs, ys = host.ray_tables(w, h)
+    frame = capi.Frame.make(w, h, classes=ALL)
+    torch.cuda.set_device(0)
+    with upload(scene, 0) as g0, upload(scene, 1) as g1:
+        want = g0.trace_frame(frame, xs, ys, LIGHT0[None, :])
+        got = g1.trace_frame(frame, xs, ys, LIGHT0[None, :])  # current device is still 0
+        assert want[0].tobytes() == got[0].tobytes() and want[1].tobytes() == got[1].tobytes()
+        rays = np.zeros(100, capi.RAY_DT)
+        rays["d"][:, 2] = 1
+        rays["o"][:, 2] = -4.9
+        rays["clip"] = np.inf
+        assert g1.intersect(rays, ALL).tobytes() == g0.intersect(rays, ALL).tobytes()
