@@ -1,21 +1,23 @@
 #!/usr/bin/env python
 """Benchmark of the hot path: one STEP = one frame of the workload through the ray-query path
-(primary rays, then one coherent shadow-ray pass per light), scene resident in HBM.
+(primary rays + one coherent shadow-ray queue per light), scene resident in HBM.
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--workload dragon4k] [--impl ours|reference]
 
-N > 1 is launched by torchrun (one rank per GPU): the scene is replicated, image tiles are interleaved
-over ranks (dodrt_frame first_tile/tile_stride), every rank traces its tiles into a compact buffer,
-the buffers are gathered on rank 0 over NVLink (NCCL) and re-assembled into the row-major frame.
-The frame is fixed, so this is STRONG scaling.
+N > 1 is launched by torchrun (one rank per GPU): the scene is replicated, image tiles are interleaved over ranks
+(dodrt_frame first_tile/tile_stride), every rank traces its tiles with ONE launch (dodrt_trace_frame_device) whose
+kernel also stores each result straight into rank 0's row-major frame buffer over NVLink (dodrt_frame_buffer_*, CUDA
+IPC): no gather, no assembly pass.  torch.distributed (NCCL) only carries the 96-byte frame-buffer descriptor, the
+barriers and the max-over-ranks of the timings.  The frame is fixed, so this is STRONG scaling.
 
-Prints ONE JSON line (rank 0).  `value` = Mrays/s (primary + shadow) with inputs resident in HBM,
-device-timed with CUDA events on the launching stream, max over ranks; `e2e` = the same metric through the
-host-buffer C-ABI call (dodrt_trace_frame: H2D of the ray tables, D2H of hit records + visibility inside
-the timed region).  `roofline` is for the dominant kernel against the measured HBM peak using the
-reference traversal's algorithmic bytes (dod_raytracer_b200/algorithmic_bytes.json); `cpu_baseline` is
-the reference's own CPU code (oracle/_ref) or, when that library did not travel, the oracle port, timed
-on this box's host cores.  `--impl reference` times that CPU implementation as the arm itself.
+Prints ONE JSON line (rank 0).  `value` = Mrays/s (primary + shadow) with inputs resident in HBM, device-timed with
+CUDA events on the launching stream, max over ranks; `e2e` = the same metric through the host-buffer C-ABI call
+(dodrt_trace_frame: H2D of the ray tables inside, every hit record and visibility byte delivered into pinned HOST
+memory inside the timed region).  `roofline` leads with the resource that binds this kernel -- instruction issue --
+and carries the HBM view (compulsory and measured bytes, and the per-ray algorithmic figure of SURVEY 8(d) as context);
+`cpu_baseline` is the reference's own CPU code (oracle/_ref) or, when that library did not travel, the oracle port,
+timed on this box's host cores.  `--impl reference` times that CPU implementation as the arm itself, without mapping
+any of the product's libraries.
 """
 import argparse
 import json
@@ -29,11 +31,13 @@ import time
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
+sys.path.insert(1, os.path.join(ROOT, "tests"))
 
 import numpy as np  # noqa: E402
 
 METRIC = "Mrays/s (primary+shadow)"
 UNIT = "Mrays/s"
+FRAME_KERNEL = "trace_frame_kernel"
 
 
 def parse_args():
@@ -44,10 +48,21 @@ def parse_args():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="dragon4k")
     ap.add_argument("--tile", default="32x32")
+    ap.add_argument("--separate", action="store_true", help="A/B: separate primary / shadow launches instead of the one-launch frame kernel")
+    ap.add_argument("--gather", default="peer", choices=["peer", "nccl"],
+                    help="N > 1: ranks store into rank 0's frame over NVLink (peer) or NCCL gather + assembly kernel (A/B, fallback)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-render", action="store_true", help="skip the reference's as-is frame (9 lights, 10 bounces)")
     return ap.parse_args()
+
+
+def config_of(w, args):
+    """The workload as BOTH arms print it (identical dicts: same config, same metric)."""
+    from dod_raytracer_b200 import workloads
+    return {"workload": w.name, "description": w.description, "mesh": workloads.mesh_label(w), "width": w.width,
+            "height": w.height, "primary_rays": w.pixels, "lights": len(w.lights) if w.shadow else 0, "classes": w.classes,
+            "l2": "GPU arm: flushed between steps (512 MiB memset outside the per-step event bracket); reference arm: CPU caches as they come"}
 
 
 # ---- clocks ---------------------------------------------------------------------------------------------
@@ -120,10 +135,10 @@ class quiet_stdout:
 
 class CpuPath:
     """oracle/_ref (the reference's translation units, kind 'reference') when it travelled, else the oracle
-    restatement (kind 'port').  Only used for cpu_baseline and --impl reference."""
+    restatement (kind 'port').  Only used for cpu_baseline, the parity check and --impl reference.  `host_arrays_fn`
+    (the product's host builder) is only called by the port when a kd-tree is needed and _ref is absent."""
 
-    def __init__(self, w, mesh_files, host_arrays_fn):
-        sys.path.insert(0, os.path.join(ROOT, "tests"))
+    def __init__(self, w, mesh_files, host_arrays_fn=None):
         import oracle_api
         self.api, self.w = oracle_api, w
         self.cores = os.cpu_count() or 1
@@ -145,7 +160,12 @@ class CpuPath:
             self.kind = "port"
             oracle_api.ensure_oracle_built()
             self.orc = oracle_api.Oracle()
-            self.scene = oracle_api.Scene.from_host_arrays(host_arrays_fn())
+            if w.mesh == "none" and w.analytic:  # config 4: no kd-tree, no product library needed
+                from scenes import analytic_scene_arrays
+                spheres, boxes = analytic_scene_arrays(4, w.analytic)
+                self.scene = oracle_api.Scene(spheres=spheres, boxes=boxes)
+            else:
+                self.scene = oracle_api.Scene.from_host_arrays(host_arrays_fn())
 
     def frame(self):
         """one full frame on all host cores: returns (seconds, rays, t [n] float32, visible [n] uint8)"""
@@ -160,7 +180,7 @@ class CpuPath:
         else:
             hits = self.orc.trace_primary(self.scene, w.width, w.height, w.classes, nthreads=self.cores)
             hit = hits["prim"] != 0xFFFFFFFF
-            t = hits["t"]
+            t = np.where(hit, hits["t"], np.float32(np.inf)).astype(np.float32)
             vis = (self.orc.trace_shadow(self.scene, w.width, w.height, w.classes, hits, self.light, nthreads=self.cores)
                    if w.shadow else np.zeros(w.pixels, np.uint8))
         dt = time.perf_counter() - t0
@@ -174,11 +194,28 @@ class CpuPath:
                 "frame_ms": seconds * 1e3}
 
 
-def run_reference_arm(args, w, mesh_files, host_arrays_fn):
+def parity_of(cpu_t, cpu_vis, gpu_hits, gpu_vis, shadow, kind, rays):
+    from dod_raytracer_b200 import capi
+    t_gpu = np.where(gpu_hits["prim"] != capi.MISS, gpu_hits["t"], np.float32(np.inf)).astype(np.float32)
+    return {"against": kind, "t_bit_mismatches": int((t_gpu.view(np.uint32) != cpu_t.view(np.uint32)).sum()),
+            "visibility_mismatches": int((gpu_vis != cpu_vis).sum()) if shadow else 0, "rays": int(rays)}
+
+
+def run_reference_arm(args, w):
+    """The reference's CPU implementation as the arm: no product library is mapped into this process (meshes come from
+    the pure-Python generator in tests/scenes.py, byte-identical to the host library's)."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    cpu = CpuPath(w, mesh_files, host_arrays_fn)
+    from scenes import workload_mesh_files_py
+    tmpdir = tempfile.mkdtemp(prefix="dodrt_bench_ref_")
+    mesh_files = workload_mesh_files_py(w, tmpdir)
+
+    def host_arrays():  # port fallback over a kd-tree only (no _ref on this box): needs the product's host builder
+        from dod_raytracer_b200 import workloads
+        return workloads.build_host_scene(w, mesh_files).arrays()
+
+    cpu = CpuPath(w, mesh_files, host_arrays)
     for _ in range(args.warmup):
         cpu.frame()
     total, rays = 0.0, 0
@@ -189,33 +226,95 @@ def run_reference_arm(args, w, mesh_files, host_arrays_fn):
     value = rays / total / 1e6
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": total / args.steps * 1e3, "higher_is_better": True, "scaling": "strong",
-            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": w.name, "description": w.description, "width": w.width, "height": w.height},
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": config_of(w, args),
             "cpu_baseline": {"value": value, "unit": UNIT, "cores": cpu.cores, "kind": cpu.kind,
-                             "sample": f"each step = the whole frame ({rays // args.steps} rays) on {cpu.cores} host threads"},
+                             "sample": f"each step = the whole frame ({rays // max(args.steps, 1)} rays) on {cpu.cores} host threads"},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     print(json.dumps(line), flush=True)
 
 
+# ---- roofline ----------------------------------------------------------------------------------------------------
+def roofline_of(w, world, shadow_rays, kernel_ms, per_pass_ms, sizes, nl, clocks, separate):
+    """What binds the frame kernel, and how far from it we are.
+
+    * issue (primary entry): warp-instructions per launch (ncu smsp__inst_executed.sum of the same kernel on the same
+      workload, profiles/traffic.json) / the LIVE launch time (CUDA events here) against 148 SMs x 4 schedulers x the SM
+      clock sampled during the run; `active_lanes` says how many of the 32 lanes an issued instruction used.
+    * hbm: the same launch time against (a) the compulsory bytes -- every node and lane of the scene once + results
+      out + hit records read back by the shadow queue -- and (b) the measured dram__bytes of the ncu capture.
+    * per_ray_cache_served: SURVEY 8(d)'s algorithmic figure (8 B/node + 288 B/lane + io per ray of the REFERENCE
+      traversal).  32 coherent rays share one fetch through L1/L2, so this is a demand on the caches, not on HBM; it is
+      context, not a roofline (it exceeds the HBM peak)."""
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        peak, peak_src = float(peaks["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
+    b_prim, b_shad = w.algorithmic_bytes(shadow_rays)
+    algorithmic = (b_prim + b_shad * nl) / world
+    scene_bytes = 8.0 * sizes.num_nodes + 288.0 * sizes.num_lanes + 128.0 * ((sizes.num_spheres + 7) // 8) + \
+        192.0 * ((sizes.num_boxes + 7) // 8)
+    io_bytes = (16.0 * w.pixels + (16.0 + 1.0) * shadow_rays * nl) / world
+    compulsory = scene_bytes + io_bytes
+    sec = kernel_ms * 1e-3
+    hbm = {"compulsory_bytes_per_launch": compulsory, "compulsory_GBs": compulsory / sec / 1e9 if sec else None,
+           "compulsory_frac": compulsory / sec / 1e9 / peak if sec else None, "peak": peak, "peak_source": peak_src,
+           "measured_dram_bytes_per_launch": None,
+           "per_ray_cache_served": {"bytes_per_launch": algorithmic, "GBs": algorithmic / sec / 1e9 if sec else None,
+                                    "note": "8 B/node + 288 B/lane + io per ray of the reference traversal (oracle-counted); "
+                                            "served by L1/L2 to 32 coherent rays at a time, not by HBM"}}
+    name = FRAME_KERNEL if not separate else ("trace_kernel<shadow>" if (nl and per_pass_ms[1] >= per_pass_ms[0]) else "trace_kernel<primary>")
+    dom_ms = kernel_ms if not separate else (per_pass_ms[1] if name.endswith("<shadow>") else per_pass_ms[0])
+    roof = {"bound": "hbm", "kernel": name, "achieved": hbm["compulsory_GBs"], "peak": peak, "unit": "GB/s",
+            "frac": hbm["compulsory_frac"], "traffic": None, "kernel_ms": dom_ms, "hbm": hbm,
+            "note": "no ncu counters for this workload/kernel in profiles/traffic.json: HBM view against compulsory bytes only"}
+    prof = os.path.join(ROOT, "profiles", "traffic.json")
+    hw = None
+    if os.path.exists(prof) and world == 1:
+        try:
+            hw = json.load(open(prof)).get(w.name, {}).get(name)
+        except Exception:
+            hw = None
+    if hw:
+        sm_mhz = (clocks or {}).get("sm_mhz") or 1965.0
+        issue_peak = 148 * 4 * sm_mhz * 1e6 / 1e9  # G warp-instructions / s
+        achieved = hw["warp_inst"] / (dom_ms * 1e-3) / 1e9
+        hbm["measured_dram_bytes_per_launch"] = hw["dram_bytes"]
+        hbm["measured_GBs"] = hw["dram_bytes"] / (dom_ms * 1e-3) / 1e9
+        hbm["measured_frac"] = hbm["measured_GBs"] / peak
+        roof.update({"bound": "issue", "achieved": achieved, "peak": issue_peak, "unit": "Gwarp-inst/s", "frac": achieved / issue_peak,
+                     "traffic": hw["dram_bytes"], "active_lanes": hw["lanes_per_inst"],
+                     "lane_frac": achieved / issue_peak * hw["lanes_per_inst"] / 32.0,
+                     "warp_inst_per_launch": hw["warp_inst"], "sm_mhz": sm_mhz,
+                     "note": "bound = instruction issue: warp-instructions per launch from the ncu capture of this kernel on this "
+                             "workload (profiles/traffic.json, " + str(hw.get("source", "profiles/")) + ") over the live CUDA-event "
+                             "launch time, against 148 SMs x 4 issue slots x the sampled SM clock; lane_frac = frac x active_lanes/32. "
+                             "The HBM view is under `hbm`: DRAM traffic is ~1 % of peak, the kernel is not memory bound"})
+    return roof
+
+
 # ---- the GPU arm ---------------------------------------------------------------------------------------------
 def main():
     args = parse_args()
-    from dod_raytracer_b200 import capi, distributed, host, workloads
+    from dod_raytracer_b200 import workloads
     w = workloads.WORKLOADS[args.workload]
+    if args.impl == "reference":
+        run_reference_arm(args, w)
+        return
+
+    from dod_raytracer_b200 import capi, distributed, host
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.separate:
+        os.environ["DODRT_FUSED"] = "0"
     tmpdir = tempfile.mkdtemp(prefix=f"dodrt_bench_{rank}_")
     mesh_files = workloads.write_mesh_files(w, tmpdir)
     t0 = time.perf_counter()
-    # GPU arm: lanes stay in creation order, Triangle::reorderLanesByIndices runs on the GPU at upload (f-4)
-    hs = workloads.build_host_scene(w, mesh_files, keep_creation_order=(args.impl != "reference"))
+    # lanes stay in creation order, Triangle::reorderLanesByIndices runs on the GPU at upload (f-4)
+    hs = workloads.build_host_scene(w, mesh_files, keep_creation_order=True)
     build_s = time.perf_counter() - t0
-
-    if args.impl == "reference":
-        run_reference_arm(args, w, mesh_files, hs.arrays)
-        return
 
     import torch
     import torch.distributed as dist
@@ -241,48 +340,80 @@ def main():
     d_xs, d_ys = torch.from_numpy(xs).to(dev), torch.from_numpy(ys).to(dev)
     lights = np.array(w.lights, np.float32)
     nl = len(lights) if w.shadow else 0
-    # per-rank result buffers (padded to rank 0's slot count so the gather is regular)
+    # per-rank result buffers (padded to rank 0's slot count so an NCCL gather, if used, is regular)
     d_hits = torch.empty((slots_rank0 if world > 1 else slots, 16), dtype=torch.uint8, device=dev)
     d_vis = torch.zeros((max(nl, 1), slots_rank0 if world > 1 else slots), dtype=torch.uint8, device=dev)
     if world > 1:
         d_hits.fill_(0xFF)
-    if world > 1 and rank == 0:
+
+    # ---- N > 1: rank 0's frame buffer, opened by every other rank over CUDA IPC ------------------------------------
+    mirror, owner_fb, gather = None, None, args.gather
+    if world > 1 and gather == "peer":
+        ok = 1
+        desc_t = torch.zeros(96, dtype=torch.uint8, device=dev)
+        try:
+            if rank == 0:
+                owner_fb = capi.FrameBuffer.create(scene, w.width, w.height, nl)
+                desc_t.copy_(torch.frombuffer(bytearray(owner_fb.export().to_bytes()), dtype=torch.uint8))
+        except Exception as exc:  # noqa: BLE001
+            print(f"bench.py: frame buffer export failed on rank 0: {exc!r}", file=sys.stderr)
+            ok = 0
+        dist.broadcast(desc_t, src=0)
+        try:
+            if rank == 0:
+                mirror = owner_fb
+            elif ok:
+                mirror = capi.FrameBuffer.open(scene, capi.FrameBufferDesc.from_bytes(bytes(desc_t.cpu().numpy())))
+        except Exception as exc:  # noqa: BLE001
+            print(f"bench.py: rank {rank} cannot open rank 0's frame buffer: {exc!r}", file=sys.stderr)
+            ok = 0
+        okt = torch.tensor([ok if mirror is not None else 0], device=dev, dtype=torch.int32)
+        dist.all_reduce(okt, op=dist.ReduceOp.MIN)
+        if int(okt.item()) == 0:
+            gather, mirror = "nccl", None  # every rank falls back together
+    if world > 1 and gather == "nccl" and rank == 0:
         g_hits = torch.empty((world, slots_rank0, 16), dtype=torch.uint8, device=dev)
         g_vis = torch.empty((world, slots_rank0), dtype=torch.uint8, device=dev)
         f_hits = torch.empty((w.pixels, 16), dtype=torch.uint8, device=dev)
         f_vis = torch.empty(w.pixels, dtype=torch.uint8, device=dev)
     flush = torch.empty(512 << 20, dtype=torch.uint8, device=dev)  # > 126 MB L2
     stream = torch.cuda.current_stream()
-
-    side = torch.cuda.Stream(device=dev) if world > 1 else None  # carries the hit-record gather
+    side = torch.cuda.Stream(device=dev) if (world > 1 and gather == "nccl") else None  # carries the hit-record gather
     hits_ready, hits_gathered = torch.cuda.Event(), torch.cuda.Event()
+    two_pass = args.separate or (world > 1 and gather == "nccl")
 
     def step(ev=None):
         sp = stream.cuda_stream
         if ev:
             ev[0].record(stream)
-        scene.trace_primary_device(frame, d_xs.data_ptr(), d_ys.data_ptr(), d_hits.data_ptr(), sp)
-        if ev:
-            ev[1].record(stream)
-        if world > 1:
-            # 94 % of the gathered bytes are the primary hit records: ship them over NVLink on a side stream
-            # WHILE the shadow pass (which only reads them) runs on the main stream
-            hits_ready.record(stream)
-            with torch.cuda.stream(side):
-                side.wait_event(hits_ready)
-                distributed.gather_to_rank0(d_hits, world, rank, g_hits if rank == 0 else None)
-                hits_gathered.record(side)
-        for l in range(nl):
-            scene.trace_shadow_device(frame, d_xs.data_ptr(), d_ys.data_ptr(), d_hits.data_ptr(), lights[l],
-                                      d_vis[l].data_ptr(), sp)
-        if ev:
-            ev[2].record(stream)
-        if world > 1:
-            distributed.gather_to_rank0(d_vis[0], world, rank, g_vis if rank == 0 else None)
-            stream.wait_event(hits_gathered)
-            if rank == 0:
-                scene.frame_assemble_device(frame, g_hits.data_ptr(), g_vis.data_ptr(), slots_rank0, f_hits.data_ptr(),
-                                            f_vis.data_ptr(), sp)
+        if not two_pass:
+            # THE product path: one launch for the rank's share, results mirrored into rank 0's frame when N > 1
+            scene.trace_frame_device(frame, d_xs.data_ptr(), d_ys.data_ptr(), lights[:nl], d_hits.data_ptr(), d_vis.data_ptr(),
+                                     mirror, sp)
+            if ev:
+                ev[1].record(stream)
+                ev[2].record(stream)
+        else:
+            scene.trace_primary_device(frame, d_xs.data_ptr(), d_ys.data_ptr(), d_hits.data_ptr(), sp)
+            if ev:
+                ev[1].record(stream)
+            if side is not None:
+                hits_ready.record(stream)
+                with torch.cuda.stream(side):
+                    side.wait_event(hits_ready)
+                    distributed.gather_to_rank0(d_hits, world, rank, g_hits if rank == 0 else None)
+                    hits_gathered.record(side)
+            for l in range(nl):
+                scene.trace_shadow_device(frame, d_xs.data_ptr(), d_ys.data_ptr(), d_hits.data_ptr(), lights[l],
+                                          d_vis[l].data_ptr(), sp)
+            if ev:
+                ev[2].record(stream)
+            if side is not None:
+                distributed.gather_to_rank0(d_vis[0], world, rank, g_vis if rank == 0 else None)
+                stream.wait_event(hits_gathered)
+                if rank == 0:
+                    scene.frame_assemble_device(frame, g_hits.data_ptr(), g_vis.data_ptr(), slots_rank0, f_hits.data_ptr(),
+                                                f_vis.data_ptr(), sp)
         if ev:
             ev[3].record(stream)
 
@@ -296,14 +427,27 @@ def main():
         flush.zero_()
         step()
     sync_all()
-    res_hits = (f_hits if (world > 1 and rank == 0) else d_hits).cpu().numpy().reshape(-1).view(capi.HIT_DT)
+
+    def assembled_frame():
+        """rank 0: the row-major frame as the run left it (hits [pixels], vis [pixels])"""
+        if world == 1:
+            return d_hits.cpu().numpy().reshape(-1).view(capi.HIT_DT), d_vis[0].cpu().numpy()
+        if gather == "nccl":
+            return f_hits.cpu().numpy().reshape(-1).view(capi.HIT_DT), f_vis.cpu().numpy()
+        hp, vp = owner_fb.pointers()
+
+        class Raw:
+            def __init__(self, ptr, n):
+                self.__cuda_array_interface__ = {"shape": (n,), "typestr": "|u1", "data": (ptr, False), "version": 2}
+        fh = torch.as_tensor(Raw(hp, w.pixels * 16), device=dev).cpu().numpy().view(capi.HIT_DT)
+        fv = torch.as_tensor(Raw(vp, w.pixels), device=dev).cpu().numpy() if nl else np.zeros(w.pixels, np.uint8)
+        return fh, fv
+
+    local_hits = d_hits.cpu().numpy().reshape(-1).view(capi.HIT_DT)
+    n_hit = torch.tensor([int((local_hits["prim"] != capi.MISS).sum())], device=dev, dtype=torch.int64)
     if world > 1:
-        n_hit_local = torch.tensor([int((d_hits.cpu().numpy().reshape(-1).view(capi.HIT_DT)["prim"] != capi.MISS).sum())],
-                                   device=dev, dtype=torch.int64)
-        dist.all_reduce(n_hit_local)
-        shadow_rays = int(n_hit_local.item()) if w.shadow else 0
-    else:
-        shadow_rays = int((res_hits["prim"] != capi.MISS).sum()) if w.shadow else 0
+        dist.all_reduce(n_hit)
+    shadow_rays = int(n_hit.item()) if w.shadow else 0
     rays_per_step = w.pixels + shadow_rays * nl
 
     # ---- timed region: exactly K steps, barrier + synchronize on both sides, device-timed per step ----------
@@ -333,33 +477,36 @@ def main():
     total_ms, prim_total, shad_total = [float(x) for x in total_ms.tolist()]
     ms_per_step = total_ms / args.steps
     value = rays_per_step / (ms_per_step * 1e-3) / 1e6
+    res_hits, res_vis = assembled_frame() if rank == 0 else (None, None)
 
-    # ---- e2e: host buffers through the C ABI (H2D + D2H inside the timed region), every rank its own tiles -------
+    # ---- e2e: host buffers through the C ABI, every rank its own tiles.  The caller's buffers are pinned, so the kernel
+    # delivers every record into them itself (dodrt_trace_frame's zero-copy path); the call returns when they are there.
     e2e = None
     if not args.no_e2e:
         h_hits = torch.empty((slots, 16), dtype=torch.uint8, pin_memory=True).numpy().reshape(-1).view(capi.HIT_DT)
         h_vis = torch.empty((max(nl, 1), slots), dtype=torch.uint8, pin_memory=True).numpy()
         h_xs = torch.from_numpy(xs).pin_memory().numpy()
         h_ys = torch.from_numpy(ys).pin_memory().numpy()
-        e2e_steps = min(args.steps, 5)
         for _ in range(2):
             scene.trace_frame(frame, h_xs, h_ys, lights[:nl], h_hits, h_vis)
         sync_all()
         t_e2e = 0.0
-        for _ in range(e2e_steps):
+        for _ in range(args.steps):
             flush.zero_()
             sync_all()
             t1 = time.perf_counter()
-            scene.trace_frame(frame, h_xs, h_ys, lights[:nl], h_hits, h_vis)  # synchronous: returns after D2H
+            scene.trace_frame(frame, h_xs, h_ys, lights[:nl], h_hits, h_vis)  # synchronous: returns when the host has it all
             t_e2e += time.perf_counter() - t1
         te = torch.tensor([t_e2e], device=dev, dtype=torch.float64)
         if world > 1:
             dist.all_reduce(te, op=dist.ReduceOp.MAX)
-        e2e_s = float(te.item()) / e2e_steps
+        e2e_s = float(te.item()) / args.steps
+        same = bool(h_hits[:slots].tobytes() == local_hits[:slots].tobytes())
         e2e = {"value": rays_per_step / e2e_s / 1e6, "unit": UNIT, "ms_per_step": e2e_s * 1e3,
                "h2d_bytes_per_step": int(xs.nbytes + ys.nbytes) * world,
                "d2h_bytes_per_step": int(w.pixels * (16 + nl)) if world == 1 else int(slots_rank0 * (16 + nl)) * world,
-               "api": "dodrt_trace_frame (host buffers, pinned)", "steps": e2e_steps}
+               "api": "dodrt_trace_frame (pinned host buffers: results stored by the kernel itself over PCIe while it traces)",
+               "steps": args.steps, "host_results_equal_device_results": same}
 
     if rank != 0:
         if world > 1:
@@ -367,58 +514,21 @@ def main():
             dist.destroy_process_group()
         return
 
-    # ---- roofline of the dominant kernel ---------------------------------------------------------------------------
-    try:
-        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
-        peak, peak_src = float(peaks["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
-    except Exception:
-        peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
-    b_prim, b_shad = w.algorithmic_bytes(shadow_rays)
-    b_prim, b_shad = b_prim / world, b_shad / world  # per launch = this rank's tiles (even split assumed)
-    k_prim, k_shad = prim_total / args.steps, shad_total / args.steps
-    dominant = "trace_kernel<shadow>" if (nl and k_shad >= k_prim) else "trace_kernel<primary>"
-    dom_bytes, dom_ms = (b_shad, k_shad) if dominant.endswith("<shadow>") else (b_prim, k_prim)
-    achieved = dom_bytes / (dom_ms * 1e-3) / 1e9 if dom_ms > 0 else 0.0
-    roofline = {"bound": "hbm", "kernel": dominant, "achieved": achieved, "peak": peak, "unit": "GB/s",
-                "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
-                "algorithmic_bytes_per_launch": dom_bytes, "kernel_ms": dom_ms,
-                "kernels": {"primary": {"ms": k_prim, "GB/s": b_prim / (k_prim * 1e-3) / 1e9 if k_prim else None},
-                            "shadow": {"ms": k_shad, "GB/s": b_shad / (k_shad * 1e-3) / 1e9 if k_shad else None}},
-                "note": "algorithmic bytes = reference traversal's 8 B/node + 288 B/lane + io (oracle-counted); "
-                        "traffic (ncu dram bytes) is in profiles/"}
-    prof = os.path.join(ROOT, "profiles", "traffic.json")
-    if os.path.exists(prof) and world == 1:
-        try:
-            hw = json.load(open(prof)).get(w.name, {}).get(dominant)
-            if hw:
-                roofline["traffic"] = hw["dram_bytes"]
-                sm_hz = (clocks or {}).get("sm_mhz") or 1965.0
-                issue_peak = 148 * 4 * sm_hz * 1e6  # warp instructions / s: 148 SMs x 4 schedulers x SM clock
-                roofline["issue"] = {"warp_inst_per_launch": hw["warp_inst"], "active_lanes_per_inst": hw["lanes_per_inst"],
-                                     "achieved_ginst_s": hw["warp_inst"] / (dom_ms * 1e-3) / 1e9,
-                                     "peak_ginst_s": issue_peak / 1e9,
-                                     "frac": hw["warp_inst"] / (dom_ms * 1e-3) / issue_peak,
-                                     "source": "ncu counters of the same kernel (profiles/traffic.json) over the live launch time"}
-        except Exception:
-            pass
-    if roofline["frac"] > 1.0:
-        roofline["note"] += ("; frac > 1 is expected here: the algorithmic bytes are PER-RAY fetches of the reference "
-                             "traversal, and the 32 coherent rays of a warp share one fetch through L1/L2 -- DRAM traffic "
-                             "(`traffic`) is <1 % of it and the kernel is bound by instruction issue (`issue`), see DESIGN.md")
+    roofline = roofline_of(w, world, shadow_rays, ms_per_step, (prim_total / args.steps, shad_total / args.steps), sizes, nl,
+                           clocks, two_pass)
 
-    # ---- CPU baseline + parity spot check (outside every timed region) ---------------------------------------------
-    cpu_baseline, parity = None, None
-    if world == 1 and not args.no_cpu_baseline:
+    # ---- CPU baseline + parity of the ASSEMBLED frame (outside every timed region), at every N --------------------------
+    cpu_baseline, parity, cpu = None, None, None
+    if not args.no_cpu_baseline:
         cpu = CpuPath(w, mesh_files, hs.arrays)
         best = None
-        for _ in range(2):
+        for _ in range(2 if world == 1 else 1):
             dt, r, t_cpu, vis_cpu = cpu.frame()
             best = dt if best is None else min(best, dt)
-        cpu_baseline = cpu.describe(best, r)
-        gpu_vis = d_vis[0].cpu().numpy() if nl else np.zeros(w.pixels, np.uint8)
-        t_gpu = np.where(res_hits["prim"] != capi.MISS, res_hits["t"], np.float32(np.inf)).astype(np.float32)
-        parity = {"against": cpu.kind, "t_bit_mismatches": int((t_gpu.view(np.uint32) != t_cpu.view(np.uint32)).sum()),
-                  "visibility_mismatches": int((gpu_vis != vis_cpu).sum()) if nl else 0, "rays": int(r)}
+        if world == 1:
+            cpu_baseline = cpu.describe(best, r)
+        parity = parity_of(t_cpu, vis_cpu, res_hits, res_vis if nl else np.zeros(w.pixels, np.uint8), nl > 0, cpu.kind, r)
+        parity["frame"] = "one GPU" if world == 1 else f"assembled from {world} ranks ({gather})"
 
     # ---- the reference's as-is frame (rayTrace, main.cpp:273-347: 9 lights, 10 bounces) at config.ini's 1920x1080 ------
     reference_frame = None
@@ -450,17 +560,22 @@ def main():
         except Exception as exc:  # never lose the headline line over the extra
             reference_frame = {"error": repr(exc)}
 
+    if world == 1:
+        how = "one launch per frame (trace_frame_kernel)" if not two_pass else "separate primary / shadow launches (A/B)"
+    elif gather == "peer":
+        how = (f"image tiles round-robin over {world} GPUs, scene replicated; one launch per rank, every result stored straight into "
+               "rank 0's row-major frame buffer over NVLink by the kernel (CUDA IPC peer mapping); no gather, no assembly pass")
+    else:
+        how = (f"image tiles round-robin over {world} GPUs, scene replicated; NCCL gather to rank 0 overlapped with the shadow pass + "
+               "dodrt_frame_assemble_device")
+    standin = w.mesh.startswith("dragon") and not os.environ.get("DODRT_DRAGON_OBJ")
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
-            "data": "synthetic",
-            "config": {"workload": w.name, "description": w.description, "mesh": workloads.mesh_label(w),
-                       "width": w.width, "height": w.height, "primary_rays": w.pixels, "shadow_rays": shadow_rays * nl,
-                       "triangles": sizes.num_triangles, "kd_nodes": sizes.num_nodes, "tri_lanes": sizes.num_lanes,
-                       "tile": args.tile, "parallelism": f"image tiles round-robin over {world} GPU(s), scene replicated"
-                                      + ("; hit-record gather to rank 0 (NCCL) overlapped with the shadow pass, "
-                                         "frame re-assembled by dodrt_frame_assemble_device" if world > 1 else ""),
-                       "l2": "flushed between steps (512 MiB memset outside the per-step event bracket)",
-                       "host_build_s": round(build_s, 2), "upload_s": round(upload_s, 2), "wall_s_timed_region": round(wall, 3)},
+            "data": "synthetic", "config": config_of(w, args),
+            "details": {"shadow_rays": shadow_rays * nl, "triangles": sizes.num_triangles, "kd_nodes": sizes.num_nodes,
+                        "tri_lanes": sizes.num_lanes, "tile": args.tile, "parallelism": how,
+                        "host_build_s": round(build_s, 2), "upload_s": round(upload_s, 2), "wall_s_timed_region": round(wall, 3),
+                        "mesh_note": "stand-in geometry: assets/dragon.obj is a missing blob in the reference" if standin else None},
             "e2e": e2e, "gpu_launches": launches, "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu_baseline,
             "parity": parity, "frame_ms": ms_per_step, "reference_frame": reference_frame}
     print(json.dumps(line), flush=True)

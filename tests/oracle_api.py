@@ -185,19 +185,30 @@ class Oracle:
 class RefLib:
     """A fresh instance of the reference (private copy of the .so => private globals)."""
 
+    _in_place_taken = False
+
     def __init__(self):
         if not have_ref():
             raise FileNotFoundError(REF_SO)
-        self._tmp = tempfile.mkdtemp(prefix="dodrt_ref_")
-        path = os.path.join(self._tmp, f"libdodrt_ref_{id(self):x}.so")
-        shutil.copy(REF_SO, path)
+        if not RefLib._in_place_taken:
+            # the first instance of a process maps oracle/_ref/libdodrt_ref.so where it lies (so that whoever audits
+            # the process's mappings sees the reference library, not an anonymous copy) ...
+            RefLib._in_place_taken = True
+            self._tmp = ""
+            path = REF_SO
+        else:
+            # ... every further instance needs its own copy = its own set of the reference's process-global scene
+            self._tmp = tempfile.mkdtemp(prefix="dodrt_ref_")
+            path = os.path.join(self._tmp, f"libdodrt_ref_{id(self):x}.so")
+            shutil.copy(REF_SO, path)
         self.lib = C.CDLL(path)
         self.lib.ref_num_spheres.restype = C.c_uint32
         self.lib.ref_add_sphere.argtypes = [C.c_void_p, C.c_float]
         self.lib.ref_add_mesh.argtypes = [C.c_char_p]
 
     def __del__(self):
-        shutil.rmtree(getattr(self, "_tmp", ""), ignore_errors=True)
+        if getattr(self, "_tmp", ""):
+            shutil.rmtree(self._tmp, ignore_errors=True)
 
     def set_config(self, width, height):
         self.lib.ref_set_config(C.c_uint(width), C.c_uint(height))

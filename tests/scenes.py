@@ -132,3 +132,62 @@ def hit_points(rays: np.ndarray, t: np.ndarray) -> np.ndarray:
     for k in range(3):
         p[:, k] = rays["o"][:, k] + (rays["d"][:, k] * t.astype(np.float32)).astype(np.float32)
     return p
+
+
+# ---- meshes for the CPU arms WITHOUT the product's libraries (bench.py --impl reference) ------------------------------
+def standin_dragon_py(n: int = 660):
+    """The deterministic stand-in for the missing assets/dragon.obj, restated with Python's libm-backed math.sin/cos in
+    the expression order of dodrt_host_standin_dragon (dod_raytracer_b200/host/dodrt_host.cpp): bit-identical positions
+    (tests/test_host_vs_ref.py::test_python_standin_dragon_is_the_host_librarys), so the reference arm of bench.py
+    builds the very same mesh without mapping libdodrt_host.so."""
+    import math
+    pi = 3.14159265358979323846
+    pos = np.empty(((n + 1) * (n + 1), 3), np.float32)
+    k = 0
+    for j in range(n + 1):
+        v = 0.02 + (pi - 0.04) * float(j) / float(n)
+        sv, cv, s5v, s29v = math.sin(v), math.cos(v), math.sin(5.0 * v), math.sin(29.0 * v)
+        for i in range(n + 1):
+            u = 2.0 * pi * float(i) / float(n)
+            r = 2.2 + 0.25 * math.sin(7.0 * u) * s5v + 0.08 * math.sin(31.0 * u + 3.0) * s29v
+            pos[k, 0] = r * sv * math.cos(u)
+            pos[k, 1] = r * cv
+            pos[k, 2] = r * sv * math.sin(u)
+            k += 1
+    stride = n + 1
+    j, i = np.meshgrid(np.arange(n, dtype=np.uint32), np.arange(n, dtype=np.uint32), indexing="ij")
+    a = (j * stride + i).ravel()
+    b, c, d = a + 1, a + stride + 1, a + stride
+    idx = np.stack([a, b, c, c, d, a], axis=1).reshape(-1, 3).astype(np.uint32)  # quad a b / d c -> (a,b,c), (c,d,a)
+    return pos, idx
+
+
+def write_dodm_py(path: str, positions: np.ndarray, indices: np.ndarray):
+    """'DODM' + u32 vertices + u32 triangles + positions + indices: the binary mesh both loaders read."""
+    positions = np.ascontiguousarray(positions, np.float32).reshape(-1, 3)
+    indices = np.ascontiguousarray(indices, np.uint32).reshape(-1, 3)
+    with open(path, "wb") as f:
+        f.write(b"DODM")
+        f.write(np.array([len(positions), len(indices)], np.uint32).tobytes())
+        f.write(positions.tobytes())
+        f.write(indices.tobytes())
+
+
+def workload_mesh_files_py(w, directory: str):
+    """dod_raytracer_b200.workloads.write_mesh_files without the host library (same bytes)."""
+    from dod_raytracer_b200 import workloads  # plain-Python constants only; nothing is dlopen'ed by this import
+    if w.mesh == "teapot":
+        return [workloads.TEAPOT_FIXTURE]
+    if w.mesh not in ("dragon", "dragon16"):
+        return []
+    real = os.environ.get("DODRT_DRAGON_OBJ")
+    if real:
+        return [real]
+    pos, idx = standin_dragon_py(w.dragon_n)
+    out = []
+    for k, (scale, tr) in enumerate(workloads._dragon_instances(w)):
+        p = (pos * np.float32(scale) + np.asarray(tr, np.float32)).astype(np.float32)
+        path = os.path.join(directory, f"{w.name}_{k}.dodm")
+        write_dodm_py(path, p, idx)
+        out.append(path)
+    return out

@@ -62,6 +62,7 @@ def teapot(request):
     """auto / plain fused / donating fused / a variant without a fused form (falls back to separate passes)"""
     g = upload(teapot_scene(full=True))
     g.set_kernel_variant(request.param)
+    g.variant = request.param
     yield g
     g.close()
 
@@ -75,7 +76,8 @@ def test_fused_launch_equals_separate_passes(teapot, w, h, tile):
     before = g.launch_count()
     got_h, got_v = _device_frame(g, frame, xs, ys, LIGHTS2, fused=True)
     assert got_h.tobytes() == want_h.tobytes() and got_v.tobytes() == want_v.tobytes()
-    assert g.launch_count() - before <= 3  # one frame kernel (+ the tile-order helper), not 1 + lights passes
+    if g.variant in (-1, 3, 7):
+        assert g.launch_count() - before <= 2  # one frame kernel (+ the tile-order helper), not 1 + lights passes
     assert want_v[0].sum() > 0 and want_v[1].tobytes() != want_v[0].tobytes()
     # primary only (no shadow queue)
     got_h0, _ = _device_frame(g, frame, xs, ys, LIGHTS2[:0])

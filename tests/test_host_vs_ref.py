@@ -126,3 +126,20 @@ def test_obj_text_loader_with_polygons_and_slashes(tmp_path):
                  "f 1/1/1 2/2/1 3/3/1 4/4/1\nf -1 1 2\nf 3//1 4//1 5//1\n")
     a = _compare_with_ref(str(p))
     assert a["num_triangles"] == 4
+
+
+def test_python_standin_dragon_is_the_host_librarys(tmp_path):
+    """bench.py's reference arm generates its meshes without the product's libraries (scenes.standin_dragon_py):
+    the files must be byte-identical to the ones the GPU arm's host library writes."""
+    import filecmp
+    from dod_raytracer_b200 import workloads
+    from scenes import standin_dragon_py, workload_mesh_files_py
+    for n in (24, 150, 660):
+        pos, idx = host.standin_dragon(n)
+        ppos, pidx = standin_dragon_py(n)
+        assert pos.tobytes() == ppos.tobytes() and idx.tobytes() == pidx.tobytes(), n
+    w = workloads.WORKLOADS["dragon4k"]
+    (tmp_path / "a").mkdir()
+    (tmp_path / "b").mkdir()
+    fa, fb = workloads.write_mesh_files(w, str(tmp_path / "a")), workload_mesh_files_py(w, str(tmp_path / "b"))
+    assert len(fa) == len(fb) == 1 and filecmp.cmp(fa[0], fb[0], shallow=False)
