@@ -9,6 +9,7 @@
 
 #include <algorithm>
 #include <atomic>
+#include <chrono>
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
@@ -140,6 +141,17 @@ struct dodrt_scene {
     size_t stVisBytes = 0;
     std::vector<cudaEvent_t> stEvents;
     size_t stEventsUsed = 0;
+    // dodrt_trace_frame with pinned host buffers can deliver the results in two ways (identical bytes): staged (device
+    // buffers + DMA copies overlapped with the shadow pass) or zero-copy (the kernel stores them over PCIe itself).
+    // Which one is faster depends on the share: SM stores reach about half the DMA bandwidth, so a whole 4K frame
+    // (141 MB) is faster staged and a 1-of-8 share (18 MB, one short launch) faster zero-copy.  The scene measures:
+    // per frame shape, calls 1-2 run staged, 3-4 zero-copy (the second of each pair is timed), then the faster stays.
+    struct HostPathChoice {
+        uint64_t key = 0;
+        uint32_t calls = 0;
+        double stagedMs = 0, zeroCopyMs = 0;
+    };
+    std::vector<HostPathChoice> hostPaths;
 };
 
 // dodrt_frame_buffer: a row-major frame in one GPU's HBM that kernels on other GPUs write into (include/dodrt.h)
@@ -452,18 +464,20 @@ int launchFrameFused(dodrt_scene *s, const dodrt_frame *frame, const float *d_xs
     }
     int rc = ensurePool(s);
     if (rc != DODRT_OK) return rc;
-    // one stream-ordered block: counters | tile_done | ready_queue | tile_order, the first three zeroed by one memset
+    // one stream-ordered block: counters | tile_order | (tile queues only: tile_done | ready_queue); one memset
     static const bool orderTiles = [] { const char *e = std::getenv("DODRT_TILE_ORDER"); return !e || std::atoi(e) != 0; }();
     const bool order = orderTiles && (frame->classes & DODRT_CLS_TREE) && s->dev.num_nodes != 0 && tiles >= 64;
+    const char *qEnv = std::getenv("DODRT_FRAME_QUEUES"); // A/B: 1 = per-tile ready queues instead of block-fused batches
+    const bool queues = qEnv && std::atoi(qEnv) != 0 && numLights != 0;
     const size_t counterBytes = sizeof(unsigned long long) * kCounterWords;
     const size_t tileBytes = sizeof(uint32_t) * (size_t)tiles;
     char *block = nullptr;
-    CUDA_TRY(cudaMallocFromPoolAsync(&block, counterBytes + tileBytes * (order ? 3 : 2), s->pool, stream));
-    cudaError_t e = cudaMemsetAsync(block, 0, counterBytes + 2 * tileBytes, stream);
+    CUDA_TRY(cudaMallocFromPoolAsync(&block, counterBytes + tileBytes * 3, s->pool, stream));
+    cudaError_t e = cudaMemsetAsync(block, 0, counterBytes + (queues ? 3 : 0) * tileBytes, stream);
     p.counter = reinterpret_cast<unsigned long long *>(block);
-    p.tile_done = reinterpret_cast<uint32_t *>(block + counterBytes);
-    p.ready_queue = p.tile_done + tiles;
-    p.tile_order = order ? p.ready_queue + tiles : nullptr;
+    p.tile_order = order ? reinterpret_cast<uint32_t *>(block + counterBytes) : nullptr;
+    p.tile_done = queues ? reinterpret_cast<uint32_t *>(block + counterBytes) + tiles : nullptr;
+    p.ready_queue = queues ? p.tile_done + tiles : nullptr;
     p.num_local_tiles = tiles;
     if (e == cudaSuccess) e = launchTraceOn(s, kModeFrame, p, stream);
     cudaFreeAsync(block, stream);
@@ -1274,11 +1288,37 @@ try {
     // there themselves, next to the device copy the shadow queue reads (TraceParams::mirror_*): 128-byte rows of hit
     // records stream over PCIe WHILE the frame is traced, nothing is copied afterwards, and the whole share is one fused
     // launch.  (Full-frame results of a tile split also need the other ranks' pixels cleared: staged path below.)
-    const char *zcEnv = std::getenv("DODRT_ZEROCOPY"); // A/B knob, read per call: 0 = always stage + copy
-    const bool zeroCopyOn = !zcEnv || std::atoi(zcEnv) != 0;
-    void *mHits = zeroCopyOn ? mappedHostPointer(hits, slots * sizeof(dodrt_hit)) : nullptr;
-    void *mVis = (zeroCopyOn && num_lights) ? mappedHostPointer(visible, slots * (size_t)num_lights) : nullptr;
-    if (e == cudaSuccess && mHits && (num_lights == 0 || mVis) && (frame->compact || frame->tile_stride == 1)) {
+    const char *zcEnv = std::getenv("DODRT_ZEROCOPY"); // read per call: 0 = always stage + copy, 1 = zero-copy whenever possible
+    const int zcMode = zcEnv ? (std::atoi(zcEnv) != 0 ? 1 : 0) : -1; // -1: measure and keep the faster (HostPathChoice)
+    void *mHits = zcMode != 0 ? mappedHostPointer(hits, slots * sizeof(dodrt_hit)) : nullptr;
+    void *mVis = (zcMode != 0 && num_lights) ? mappedHostPointer(visible, slots * (size_t)num_lights) : nullptr;
+    bool zeroCopy = mHits && (num_lights == 0 || mVis) && (frame->compact || frame->tile_stride == 1);
+    dodrt_scene::HostPathChoice *choice = nullptr;
+    if (zeroCopy && zcMode < 0) {
+        const uint64_t key = (slots << 8) ^ ((uint64_t)num_lights << 3) ^ (frame->compact ? 4u : 0u) ^ ((uint64_t)frame->tile_stride << 40);
+        for (auto &c : s->hostPaths) {
+            if (c.key == key) choice = &c;
+        }
+        if (!choice) {
+            s->hostPaths.emplace_back();
+            choice = &s->hostPaths.back();
+            choice->key = key;
+        }
+        const uint32_t call = choice->calls++;
+        if (call >= 4) {
+            zeroCopy = choice->zeroCopyMs < choice->stagedMs;
+            choice = nullptr; // decided: nothing left to measure
+        } else {
+            zeroCopy = call >= 2;
+        }
+    }
+    const auto hostT0 = std::chrono::steady_clock::now();
+    auto noteTime = [&](bool wasZeroCopy) {
+        if (!choice || (choice->calls != 2 && choice->calls != 4)) return; // the second call of each pair counts
+        const double ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - hostT0).count();
+        (wasZeroCopy ? choice->zeroCopyMs : choice->stagedMs) = ms;
+    };
+    if (e == cudaSuccess && zeroCopy) {
         Mirror m;
         m.hits = static_cast<dodrt_hit *>(mHits);
         m.visible = static_cast<uint8_t *>(mVis);
@@ -1288,6 +1328,7 @@ try {
         cudaError_t es = cudaStreamSynchronize(st);
         if (rc != DODRT_OK) return rc;
         if (es != cudaSuccess) return fail(DODRT_E_CUDA, "dodrt_trace_frame: %s", cudaGetErrorString(es));
+        noteTime(true);
         return DODRT_OK;
     }
     if (e == cudaSuccess && !frame->compact) {
@@ -1352,6 +1393,7 @@ try {
     if (e == cudaSuccess) e = ec;
     if (e == cudaSuccess) e = es;
     if (e != cudaSuccess) return fail(DODRT_E_CUDA, "dodrt_trace_frame: %s", cudaGetErrorString(e));
+    noteTime(false);
     return DODRT_OK;
 }
 DODRT_CATCH

@@ -715,10 +715,11 @@ __global__ void __launch_bounds__(128, VARIANT >= kDonateVariant ? 5 : DODRT_MIN
 // Two work queues.  Queue 1 holds the primary batches (8x4 pixel blocks, tiles in heavy-first order); queue 2 holds the
 // shadow batches -- still a separate, coherent any-hit pass over 8x4 blocks (main.cpp:182-219 per pixel), but a tile's
 // shadow batches become claimable as soon as ITS primary records are complete instead of after the whole primary pass:
-//   * the warp that finishes the last primary batch of a tile (tile_done[t] reaches batches-per-tile) appends the tile to
-//     ready_queue;
-//   * shadow batch number q belongs to the (q / (batches-per-tile * lights))-th tile of ready_queue; a warp that claims a
-//     batch whose tile is not published yet waits for it (the tile's primary batches are in flight on resident warps).
+//   * the warp that finishes the last primary batch of a tile (tile_done[t] reaches batches-per-tile) classifies the tile
+//     (heavy: a shadow ray enters the kd-tree bounds) and appends it to the heavy or the light ready list (publish_tile);
+//   * a warp that has run out of primary batches claims shadow batches of published tiles, heavy list first
+//     (claim_shadow_batch); when nothing is claimable yet it waits: the missing tiles' primary batches are in flight on
+//     resident warps.
 // The tail of the primary queue (its slowest batches) therefore overlaps shadow work, and the pass has ONE ramp and ONE
 // tail instead of two of each with a grid-wide barrier in between -- which is what limited an 8-way split of a 4K frame
 // (0.26 + 0.53 ms per rank against 0.47 ms ideal).  Per pixel nothing changes: same primary query, same shadow ray from
@@ -726,120 +727,90 @@ __global__ void __launch_bounds__(128, VARIANT >= kDonateVariant ? 5 : DODRT_MIN
 // Donation (VARIANT 7): only shadow rays are ever suspended.  A helper exists once the shadow queue is exhausted, and the
 // last shadow claims wait for the last tiles, whose primary batches may still run: those must not give rays away (a
 // tile would be published while a record is still pending), hence allowDonate = false in queue 1.
-template <int VARIANT>
-__global__ void __launch_bounds__(128, VARIANT >= kDonateVariant ? 5 : DODRT_MINBLOCKS) trace_frame_kernel(const TraceParams p)
+// One work item of trace_frame_kernel: SHADOW = false: a primary batch of queue 1; true: a shadow batch of queue 2.
+// Returns false when the queue is exhausted.
+template <int VARIANT, bool SHADOW> __device__ __forceinline__ bool frame_batch(const TraceParams &p)
 {
     const uint32_t lane = threadIdx.x & 31u;
-    if (VARIANT == kDonateVariant && p.donate_slots != nullptr && lane == 0) {
-        atomicAdd(p.counter + kDonateStarted, 1ull); // see donate_helper_loop
-    }
     const dodrt_frame &f = p.frame;
     const uint32_t tilePixels = f.tile_w * f.tile_h;
     const uint32_t bpt = tilePixels >> 5; // batches per tile
-    const uint32_t bpr = f.tile_w >> 3;   // 8x4 blocks per tile row
-    const uint32_t perTile = bpt * p.num_lights;
-    const float o[3] = {f.origin[0], f.origin[1], f.origin[2]};
-    bool primaryLeft = true;
-    // ONE loop and one call site of the query for both queues (half the code of two specialised loops: the hot
-    // traversal is the same, only the ray set-up and the result differ)
-    for (;;) {
+    uint32_t col = 0, row = 0, localTile = 0, light = 0;
+    uint64_t slot = 0;
+    bool inside;
+    if (!SHADOW) {
         unsigned long long base = 0;
-        if (primaryLeft) {
-            if (lane == 0) {
-                base = atomicAdd(p.counter, 32ull);
-            }
-            base = __shfl_sync(0xffffffffu, base, 0);
-            primaryLeft = base < p.count;
+        if (lane == 0) {
+            base = atomicAdd(p.counter, 32ull);
         }
-        if (!primaryLeft) {
-            if (lane == 0) {
-                base = atomicAdd(p.counter + kShadowNext, 32ull);
-            }
-            base = __shfl_sync(0xffffffffu, base, 0);
-            if (base >= p.shadow_count) {
-                break;
-            }
+        base = __shfl_sync(0xffffffffu, base, 0);
+        if (base >= p.count) {
+            return false;
         }
-        const bool shadow = !primaryLeft;
-        uint32_t col = 0, row = 0, localTile = 0, light = 0;
-        uint64_t slot = 0;
-        bool inside;
-        if (!shadow) { // ---- queue 1: a primary batch
-            inside = slot_to_pixel(f, p.tiles_x, p.tile_order, base + lane, col, row, slot);
-            localTile = (uint32_t)(slot / tilePixels);
-        } else { // ---- queue 2: a shadow batch of a complete tile, one light after the other per tile
-            const uint64_t seq = base >> 5;
-            const uint32_t readyIdx = (uint32_t)(seq / perTile);
-            const uint32_t rem = (uint32_t)(seq - (uint64_t)readyIdx * perTile);
-            light = rem / bpt;
-            const uint32_t block = rem - light * bpt;
-            if (lane == 0) {
-                unsigned ns = 100;
-                while ((localTile = *reinterpret_cast<const volatile uint32_t *>(p.ready_queue + readyIdx)) == 0u) {
-                    __nanosleep(ns);
-                    ns = ns < 1600u ? ns * 2u : ns;
-                }
-            }
-            localTile = __shfl_sync(0xffffffffu, localTile, 0) - 1u;
-            __threadfence(); // acquire side of the tile's publication
-            const uint32_t tile = f.first_tile + localTile * f.tile_stride;
-            const uint32_t tx = tile % p.tiles_x, ty = tile / p.tiles_x;
-            const uint32_t bx = block % bpr, by = block / bpr;
-            col = tx * f.tile_w + bx * 8 + (lane & 7u);
-            row = ty * f.tile_h + by * 4 + (lane >> 3);
-            inside = col < f.width && row < f.height;
-            slot = (uint64_t)localTile * tilePixels + block * 32u + lane;
+        inside = slot_to_pixel(f, p.tiles_x, p.tile_order, base + lane, col, row, slot);
+        localTile = (uint32_t)(slot / tilePixels);
+    } else {
+        // the batch's tile: the (seq / batches-per-tile / lights)-th that became complete; lights one after the other
+        const uint32_t perTile = bpt * p.num_lights;
+        const uint32_t bpr = f.tile_w >> 3; // 8x4 blocks per tile row
+        unsigned long long base = 0;
+        if (lane == 0) {
+            base = atomicAdd(p.counter + kShadowNext, 32ull);
         }
-        const uint64_t pixel = (uint64_t)row * f.width + col;
-        const uint64_t idx = f.compact ? slot : pixel;
-        const uint64_t midx = p.mirror_by_pixel ? pixel : idx;
-        float rd[3] = {0.0f, 0.0f, 1.0f}, ro[3] = {o[0], o[1], o[2]};
-        float clip = kInfinity;
-        bool cast = inside;
-        // (a mirror with the local layout also receives the padded slots of edge tiles, like the local buffer)
-        const bool mirrored = inside || (f.compact && !p.mirror_by_pixel);
-        uint64_t out = idx, mirror = (p.mirror_hits != nullptr && mirrored) ? midx : kNoMirror;
-        if (inside) {
-            primary_dir(__ldg(p.xs + col), __ldg(p.ys + row), rd);
+        base = __shfl_sync(0xffffffffu, base, 0);
+        if (base >= p.shadow_count) {
+            return false;
         }
-        if (shadow) {
-            out = (uint64_t)light * p.visible_light_stride + idx;
-            mirror = (p.mirror_visible != nullptr && mirrored) ? (uint64_t)light * p.mirror_light_stride + midx : kNoMirror;
-            cast = false;
-            clip = 0.0f;
-            if (inside) {
-                const float4 ph = __ldcg(reinterpret_cast<const float4 *>(p.hits) + idx); // written in this launch: L2, not L1
-                if (__float_as_uint(ph.y) != DODRT_MISS) {
-                    const float light3[3] = {p.lights[light][0], p.lights[light][1], p.lights[light][2]};
-                    float so[3], sd[3];
-                    shadow_ray(o, rd, ph.x, light3, so, sd, clip);
-                    ro[0] = so[0], ro[1] = so[1], ro[2] = so[2];
-                    rd[0] = sd[0], rd[1] = sd[1], rd[2] = sd[2];
-                    cast = true;
-                }
+        const uint64_t seq = base >> 5;
+        const uint32_t entry = (uint32_t)(seq / perTile);
+        const uint32_t rem = (uint32_t)(seq - (uint64_t)entry * perTile);
+        light = rem / bpt;
+        const uint32_t block = rem - light * bpt;
+        if (lane == 0) { // not published yet: the tile's primary batches are in flight on resident warps
+            unsigned ns = 100;
+            while ((localTile = *reinterpret_cast<const volatile uint32_t *>(p.ready_queue + entry)) == 0u) {
+                __nanosleep(ns);
+                ns = ns < 1600u ? ns * 2u : ns;
             }
         }
-        Hit h;
-        bool donated = false;
-        const bool found = query<VARIANT>(p.scene, p.classes, cast, ro, rd, shadow, clip, h, &p, shadow ? kFinishVisible : kFinishRecord,
-                                          out, &donated, mirror, shadow);
-        if ((inside || f.compact) && !donated) { // padded slots of edge tiles read as "miss" / "not visible"
-            if (shadow) {
-                const uint8_t v = (cast && !found) ? 1 : 0;
-                p.visible[out] = v;
-                if (mirror != kNoMirror) {
-                    p.mirror_visible[mirror] = v;
-                }
-            } else {
-                const float4 r = make_float4(h.t, __uint_as_float(h.prim), h.u, h.v);
-                reinterpret_cast<float4 *>(p.hits)[out] = r;
-                if (mirror != kNoMirror) {
-                    reinterpret_cast<float4 *>(p.mirror_hits)[mirror] = r;
-                }
+        localTile = __shfl_sync(0xffffffffu, localTile, 0) - 1u;
+        __threadfence(); // acquire side of the tile's publication
+        const uint32_t tile = f.first_tile + localTile * f.tile_stride;
+        const uint32_t tx = tile % p.tiles_x, ty = tile / p.tiles_x;
+        const uint32_t bx = block % bpr, by = block / bpr;
+        col = tx * f.tile_w + bx * 8 + (lane & 7u);
+        row = ty * f.tile_h + by * 4 + (lane >> 3);
+        inside = col < f.width && row < f.height;
+        slot = (uint64_t)localTile * tilePixels + block * 32u + lane;
+    }
+    const uint64_t pixel = (uint64_t)row * f.width + col;
+    const uint64_t idx = f.compact ? slot : pixel;
+    const uint64_t midx = p.mirror_by_pixel ? pixel : idx;
+    // (a mirror with the local layout also receives the padded slots of edge tiles, like the local buffer)
+    const bool mirrored = inside || (f.compact && !p.mirror_by_pixel);
+    const float o[3] = {f.origin[0], f.origin[1], f.origin[2]};
+    float d[3] = {0.0f, 0.0f, 1.0f};
+    if (inside) {
+        primary_dir(__ldg(p.xs + col), __ldg(p.ys + row), d);
+    }
+    Hit h;
+    bool donated = false;
+    if (!SHADOW) {
+        const uint64_t mirror = (p.mirror_hits != nullptr && mirrored) ? midx : kNoMirror;
+        // Rays of queue 1 are only given away when there is no queue 2 (a primary-only frame): a tile must not be
+        // published while one of its records is still pending in the donation queue.  (With a shadow queue helpers
+        // only exist once every tile has been published anyway.)
+        query<VARIANT>(p.scene, p.classes, inside, o, d, false, kInfinity, h, &p, kFinishRecord, idx, &donated, mirror,
+                       p.shadow_count == 0);
+        if ((inside || f.compact) && !donated) { // padded slots of edge tiles read as "miss"
+            const float4 r = make_float4(h.t, __uint_as_float(h.prim), h.u, h.v);
+            reinterpret_cast<float4 *>(p.hits)[idx] = r;
+            if (mirror != kNoMirror) {
+                reinterpret_cast<float4 *>(p.mirror_hits)[mirror] = r;
             }
         }
-        if (!shadow && p.shadow_count != 0) {
-            // publish: every lane's record must be visible before the tile can be counted complete
+        if (p.shadow_count != 0) {
+            // every lane's record must be visible before the tile can be counted complete
             __threadfence();
             __syncwarp();
             if (lane == 0 && atomicAdd(p.tile_done + localTile, 1u) + 1u == bpt) {
@@ -847,6 +818,118 @@ __global__ void __launch_bounds__(128, VARIANT >= kDonateVariant ? 5 : DODRT_MIN
                 const unsigned long long k = atomicAdd(p.counter + kReadyTail, 1ull);
                 *reinterpret_cast<volatile uint32_t *>(p.ready_queue + k) = localTile + 1u;
             }
+        }
+    } else {
+        const uint64_t out = (uint64_t)light * p.visible_light_stride + idx;
+        const uint64_t mirror = (p.mirror_visible != nullptr && mirrored) ? (uint64_t)light * p.mirror_light_stride + midx : kNoMirror;
+        bool cast = false;
+        float so[3] = {0.0f, 0.0f, 0.0f}, sd[3] = {0.0f, 0.0f, 1.0f}, sclip = 0.0f;
+        if (inside) {
+            const float4 ph = __ldcg(reinterpret_cast<const float4 *>(p.hits) + idx); // written in this launch: L2, not L1
+            if (__float_as_uint(ph.y) != DODRT_MISS) {
+                const float light3[3] = {p.lights[light][0], p.lights[light][1], p.lights[light][2]};
+                shadow_ray(o, d, ph.x, light3, so, sd, sclip);
+                cast = true;
+            }
+        }
+        const bool blocked = query<VARIANT>(p.scene, p.classes, cast, so, sd, true, sclip, h, &p, kFinishVisible, out, &donated, mirror);
+        if ((inside || f.compact) && !donated) { // padded slots read as "not visible"
+            const uint8_t v = (cast && !blocked) ? 1 : 0;
+            p.visible[out] = v;
+            if (mirror != kNoMirror) {
+                p.mirror_visible[mirror] = v;
+            }
+        }
+    }
+    return true;
+}
+
+// BLOCK-FUSED work item (the default frame kernel): one 8x4 pixel block end to end -- its primary batch, then, from the
+// hit records still in registers, its shadow batch for every light (each a separate, coherent any-hit query over the
+// same 32 pixels: main.cpp:182-219).  No warp ever waits for another one: there is no readiness bookkeeping, no second
+// claim and no re-read of the hit records; while one warp is in a long primary batch the others are in shadow batches,
+// so the tails of the two kinds of work overlap like with the tile queues above.  hitPoint = o + d*t is computed from
+// the same float the record holds, so the shadow ray has the same bits.
+template <int VARIANT> __device__ __forceinline__ bool frame_block(const TraceParams &p)
+{
+    const uint32_t lane = threadIdx.x & 31u;
+    const dodrt_frame &f = p.frame;
+    unsigned long long base = 0;
+    if (lane == 0) {
+        base = atomicAdd(p.counter, 32ull);
+    }
+    base = __shfl_sync(0xffffffffu, base, 0);
+    if (base >= p.count) {
+        return false;
+    }
+    uint32_t col = 0, row = 0;
+    uint64_t slot = 0;
+    const bool inside = slot_to_pixel(f, p.tiles_x, p.tile_order, base + lane, col, row, slot);
+    const uint64_t pixel = (uint64_t)row * f.width + col;
+    const uint64_t idx = f.compact ? slot : pixel;
+    const uint64_t midx = p.mirror_by_pixel ? pixel : idx;
+    // (a mirror with the local layout also receives the padded slots of edge tiles, like the local buffer)
+    const bool mirrored = inside || (f.compact && !p.mirror_by_pixel);
+    const float o[3] = {f.origin[0], f.origin[1], f.origin[2]};
+    float d[3] = {0.0f, 0.0f, 1.0f};
+    if (inside) {
+        primary_dir(__ldg(p.xs + col), __ldg(p.ys + row), d);
+    }
+    Hit h;
+    bool donated = false;
+    {
+        const uint64_t mirror = (p.mirror_hits != nullptr && mirrored) ? midx : kNoMirror;
+        // a primary ray can only be given away when nothing follows it (no lights)
+        query<VARIANT>(p.scene, p.classes, inside, o, d, false, kInfinity, h, &p, kFinishRecord, idx, &donated, mirror, p.num_lights == 0);
+        if ((inside || f.compact) && !donated) { // padded slots of edge tiles read as "miss"
+            const float4 r = make_float4(h.t, __uint_as_float(h.prim), h.u, h.v);
+            reinterpret_cast<float4 *>(p.hits)[idx] = r;
+            if (mirror != kNoMirror) {
+                reinterpret_cast<float4 *>(p.mirror_hits)[mirror] = r;
+            }
+        }
+    }
+    const bool cast = inside && h.prim != DODRT_MISS;
+    const float tHit = h.t;
+    for (uint32_t light = 0; light < p.num_lights; light++) {
+        const uint64_t out = (uint64_t)light * p.visible_light_stride + idx;
+        const uint64_t mirror = (p.mirror_visible != nullptr && mirrored) ? (uint64_t)light * p.mirror_light_stride + midx : kNoMirror;
+        float so[3] = {0.0f, 0.0f, 0.0f}, sd[3] = {0.0f, 0.0f, 1.0f}, sclip = 0.0f;
+        if (cast) {
+            const float light3[3] = {p.lights[light][0], p.lights[light][1], p.lights[light][2]};
+            shadow_ray(o, d, tHit, light3, so, sd, sclip);
+        }
+        Hit hs;
+        bool given = false;
+        const bool blocked = query<VARIANT>(p.scene, p.classes, cast, so, sd, true, sclip, hs, &p, kFinishVisible, out, &given, mirror);
+        if ((inside || f.compact) && !given) { // padded slots read as "not visible"
+            const uint8_t v = (cast && !blocked) ? 1 : 0;
+            p.visible[out] = v;
+            if (mirror != kNoMirror) {
+                p.mirror_visible[mirror] = v;
+            }
+        }
+    }
+    return true;
+}
+
+template <int VARIANT, bool TILE_QUEUES>
+__global__ void __launch_bounds__(128, VARIANT >= kDonateVariant ? 5 : DODRT_MINBLOCKS) trace_frame_kernel(const TraceParams p)
+{
+    const uint32_t lane = threadIdx.x & 31u;
+    if (VARIANT == kDonateVariant && p.donate_slots != nullptr && lane == 0) {
+        atomicAdd(p.counter + kDonateStarted, 1ull); // see donate_helper_loop
+    }
+    // Two loops, each with its own SPECIALISED copy of the query (closest-hit with the full hit record / any-hit with
+    // nothing but the boolean): one call site with a run-time any-hit flag cost the shadow queue 40 % (the any-hit
+    // kernel drops all (t, u, v, id) bookkeeping and fits its registers; measured 5.24 vs 3.82 ms per dragon4k frame).
+    if (TILE_QUEUES) {
+        while (frame_batch<VARIANT, false>(p)) {
+        }
+        while (frame_batch<VARIANT, true>(p)) {
+        }
+    } else {
+        while (frame_block<VARIANT>(p)) {
         }
     }
     if (VARIANT == kDonateVariant && p.donate_slots != nullptr) {
@@ -944,7 +1027,12 @@ template <int MODE, int VARIANT> cudaError_t config_for(int device, LaunchConfig
     cudaError_t e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
     if (e != cudaSuccess) return e;
     if constexpr (MODE == kModeFrame) { // the fused kernel exists as the plain voted kernel and as the donating one
-        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, trace_frame_kernel<(VARIANT == kDonateVariant ? kDonateVariant : 3)>, 128, 0);
+        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, trace_frame_kernel<(VARIANT == kDonateVariant ? kDonateVariant : 3), false>, 128, 0);
+        int perSmQ = 0;
+        if (e == cudaSuccess) {
+            e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSmQ, trace_frame_kernel<(VARIANT == kDonateVariant ? kDonateVariant : 3), true>, 128, 0);
+        }
+        if (perSmQ < perSm) perSm = perSmQ; // one launch shape (and one donation queue size) for both forms
     } else if constexpr (VARIANT == 4 && MODE != kModeShadowRays) {
         e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, trace_kernel_pool<MODE>, 128, 0);
     } else if constexpr (VARIANT == 4) { // the pool kernel has no explicit-ray shadow mode: variant 3 serves it
@@ -962,7 +1050,11 @@ template <int MODE, int VARIANT> cudaError_t config_for(int device, LaunchConfig
 template <int MODE, int VARIANT> void launch_one(const TraceParams &p, const LaunchConfig &cfg, cudaStream_t stream)
 {
     if constexpr (MODE == kModeFrame) {
-        trace_frame_kernel<(VARIANT == kDonateVariant ? kDonateVariant : 3)><<<cfg.grid, cfg.block, 0, stream>>>(p);
+        if (p.tile_done != nullptr) { // tile queues (A/B form, DODRT_FRAME_QUEUES=1)
+            trace_frame_kernel<(VARIANT == kDonateVariant ? kDonateVariant : 3), true><<<cfg.grid, cfg.block, 0, stream>>>(p);
+        } else {
+            trace_frame_kernel<(VARIANT == kDonateVariant ? kDonateVariant : 3), false><<<cfg.grid, cfg.block, 0, stream>>>(p);
+        }
     } else if constexpr (VARIANT == 4 && MODE != kModeShadowRays) {
         trace_kernel_pool<MODE><<<cfg.grid, cfg.block, 0, stream>>>(p);
     } else if constexpr (VARIANT == 4) {

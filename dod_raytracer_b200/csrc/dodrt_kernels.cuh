@@ -58,7 +58,8 @@ struct TraceParams {
     uint32_t mirror_by_pixel;
     // kModeFrame: the lights of the shadow queue, visible[l * visible_light_stride + slot]; per-tile bookkeeping that
     // makes a tile's shadow batches claimable once its primary records are complete (all zeroed before the launch):
-    // tile_done[t] = primary batches of local tile t finished; ready_queue[k] = 1 + the k-th tile that became complete
+    // tile_done[t] = primary batches of local tile t finished; ready_queue[k] = 1 + the k-th tile that became complete.
+    // nullptr = the block-fused form of the frame kernel (no queues at all)
     uint32_t num_lights;
     float lights[16][3];
     uint64_t visible_light_stride;
@@ -68,7 +69,7 @@ struct TraceParams {
 };
 
 // counters (one 256-B block per launch): [0] next work item, [1]/[2] heavy/light tiles placed (order_tiles_kernel);
-// kModeFrame: [3] next shadow item, [4] tiles published in ready_queue;
+// kModeFrame with tile queues: [3] next shadow item, [4] tiles published in ready_queue;
 // on their own 128-B line, away from the work counter every warp hammers: [16] warps that left the main loop,
 // [17] donation tickets taken by helpers, [18] donation slots reserved by donors, [19] warps that entered the kernel
 // (dodrt_donate.inl)

@@ -82,6 +82,13 @@ def test_fused_launch_equals_separate_passes(teapot, w, h, tile):
     # primary only (no shadow queue)
     got_h0, _ = _device_frame(g, frame, xs, ys, LIGHTS2[:0])
     assert got_h0.tobytes() == want_h.tobytes()
+    # A/B form of the frame kernel: per-tile ready queues instead of block-fused batches
+    os.environ["DODRT_FRAME_QUEUES"] = "1"
+    try:
+        q_h, q_v = _device_frame(g, frame, xs, ys, LIGHTS2, fused=True)
+    finally:
+        os.environ.pop("DODRT_FRAME_QUEUES", None)
+    assert q_h.tobytes() == want_h.tobytes() and q_v.tobytes() == want_v.tobytes()
 
 
 def test_fused_tile_split_with_frame_buffer_mirror(teapot):
@@ -121,7 +128,7 @@ def test_host_buffers_zero_copy_equals_staged(teapot, monkeypatch):
         slots = capi.frame_local_pixels(frame) if frame.compact else w * h
         monkeypatch.setenv("DODRT_ZEROCOPY", "0")
         want_h, want_v = g.trace_frame(frame, xs, ys, LIGHTS2)
-        monkeypatch.delenv("DODRT_ZEROCOPY")
+        monkeypatch.setenv("DODRT_ZEROCOPY", "1")
         ph = torch.full((slots, 16), 0x5A, dtype=torch.uint8).pin_memory().numpy().reshape(-1).view(capi.HIT_DT)
         pv = torch.full((2, slots), 0x5A, dtype=torch.uint8).pin_memory().numpy()
         before = g.launch_count()
@@ -132,6 +139,13 @@ def test_host_buffers_zero_copy_equals_staged(teapot, monkeypatch):
         g.trace_frame(frame, xs, ys, LIGHTS2[:0], ph, None)
         assert ph.tobytes() == want_h.tobytes()
         assert g.launch_count() > before
+        # default: the scene measures both ways for this frame shape (2 + 2 calls) and keeps the faster -- same bytes always
+        monkeypatch.delenv("DODRT_ZEROCOPY")
+        for _ in range(6):
+            ph[:] = np.zeros(1, capi.HIT_DT)
+            pv[:] = 7
+            g.trace_frame(frame, xs, ys, LIGHTS2, ph, pv)
+            assert ph.tobytes() == want_h.tobytes() and pv.tobytes() == want_v.tobytes()
 
 
 def test_frame_buffer_shared_with_another_process(tmp_path):
