@@ -427,8 +427,10 @@ int launchFrameFused(dodrt_scene *s, const dodrt_frame *frame, const float *d_xs
                      cudaStream_t stream, bool *done)
 {
     *done = false;
-    const char *fusedEnv = std::getenv("DODRT_FUSED"); // A/B knob, read per call: 0 = separate primary / shadow launches
-    const bool fusedOn = !fusedEnv || std::atoi(fusedEnv) != 0;
+    // A/B knob, read per call: 1 = the one-launch frame kernels.  Default: separate primary / shadow passes, which are
+    // faster at every share size (profiles/r02_frame_kernel_ab.txt)
+    const char *fusedEnv = std::getenv("DODRT_FUSED");
+    const bool fusedOn = fusedEnv && std::atoi(fusedEnv) != 0;
     if (!fusedOn || numLights > (uint32_t)kMaxLights) return DODRT_OK;
     TraceParams p{};
     p.scene = s->dev;
@@ -593,6 +595,13 @@ try {
         s->dev.donate_poll = poll ? (uint32_t)std::max(1, std::atoi(poll)) : 32u;
         const char *refill = std::getenv("DODRT_POOL_REFILL");
         s->dev.pool_refill = refill ? (uint32_t)std::min(32, std::max(1, std::atoi(refill))) : 32u;
+        const char *fork = std::getenv("DODRT_FORK_POLL");
+        // measured on a 1-of-8 share of dragon4k (profiles/r02_donation_fork.txt): work splitting of resumed any-hit rays
+        // loses (0.71 -> 0.74-0.79 ms: the forks take the waiting helpers away from the donors), so it is off; 512 waiting
+        // helpers serve the donors as well as all ~2900 idle warps do, and poll six times less
+        s->dev.fork_poll = fork ? (uint32_t)std::max(0, std::atoi(fork)) : 0u;
+        const char *limit = std::getenv("DODRT_HELPER_LIMIT");
+        s->dev.helper_limit = limit ? (uint32_t)std::max(1, std::atoi(limit)) : 512u;
         const char *always = std::getenv("DODRT_DONATE_ALWAYS");
         s->dev.tune[3] = (always && std::atoi(always) != 0) ? 1u : 0u;
     }

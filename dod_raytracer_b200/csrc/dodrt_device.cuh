@@ -65,6 +65,10 @@ struct DeviceScene {
     uint32_t donate_poll;
     // variant 4: idle lanes that send the warp back to top up its ray pool (32 = only when every ray is finished)
     uint32_t pool_refill;
+    // variant 7: resume steps between two fork polls of a resumed any-hit ray (0 = no work splitting), and how many
+    // helpers may wait for a ray at a time (further idle warps leave the kernel)
+    uint32_t fork_poll;
+    uint32_t helper_limit;
 };
 
 struct Hit {

@@ -18,7 +18,24 @@
 // blocks may not be resident yet, and they could never start while everybody spins.  A block that starts late finds
 // the work counter exhausted and has nothing to donate, so the pass ends when every warp that entered has left its
 // main loop and the queue is drained (tests/test_gpu_parity.py::test_concurrent_donating_launches).
+//
+// WORK SPLITTING of a resumed any-hit ray (round 2, profiles/r02_donation_fork.txt).  What was left of a short pass was a
+// chain-length bound: one resumed ray walks ~500 dependent node / leaf steps at L2 latency (~0.2 us each) whoever executes
+// it, while thousands of helpers wait.  For an any-hit query the answer is an OR over the leaves the no-hit traversal
+// visits (kdtree.cpp:338-341), so the sub-trees on the ray's short stack are INDEPENDENT jobs: a helper that
+// sees other helpers waiting (head > tail) FORKS -- it pushes its oldest stack entries as new queue slots (same ray, node
+// = the entry, empty stack) and keeps the rest.  Pieces fork again when their own stacks grow.  The result needs no join:
+// the first fork writes the optimistic answer ("visible" / "miss") once, before the children are published, and from
+// then on a piece only ever writes "blocked" / "hit"; a piece that sees the answer already decided stops.
+// Termination with forking helpers: a waiting helper may leave only in a QUIESCENT state -- every warp has left its main
+// loop, and every reserved slot has been completely served (kDonateServed == tail: nobody is resuming, so nobody can
+// fork) -- and then only if the final tail does not cover its ticket.  The state is detected by whoever causes it (the
+// last warp to leave its main loop / the helper that serves the last slot: donate_check_quiescent) and announced in ONE
+// word on a line nobody writes any more; the thousands of waiting helpers poll that word and their own ready word, not
+// the queue's counters -- with every helper reading finished / started / served / tail each round, the counter line
+// saturated and the donors' own polls and reservations took microseconds (1-of-8 share: 0.71 -> 1.04 ms).
 enum FinishKind : uint32_t { kFinishRecord = 0, kFinishAnyRecord = 1, kFinishVisible = 2 };
+constexpr uint32_t kFlagAny = 1u, kFlagFound = 2u, kFlagForked = 4u; // slot word 7, bits 0-2; FinishKind in bits 3-4
 
 // What remains to be done with the kd-tree's answer for one ray (main.cpp:320-325 / 209-217 as the trace kernel
 // applies them): where the result goes and what it is when the tree finds nothing.
@@ -99,7 +116,7 @@ __device__ __noinline__ void donate_store(uint32_t *slots, uint32_t *ready, uint
 {
     float4 *w = reinterpret_cast<float4 *>(slots + (size_t)slot * kDonateSlotWords);
     w[0] = r.w[0];
-    w[1] = make_float4(r.w[1].x, r.w[1].y, r.w[1].z, __uint_as_float(__float_as_uint(r.w[1].w) | (fin->kind << 2)));
+    w[1] = make_float4(r.w[1].x, r.w[1].y, r.w[1].z, __uint_as_float(__float_as_uint(r.w[1].w) | (fin->kind << 3)));
     w[2] = r.w[2];
     w[3] = make_float4(fin->pre[0], fin->pre[1], fin->pre[2], fin->pre[3]);
     w[4] = r.w[4];
@@ -141,7 +158,7 @@ __device__ __forceinline__ void donate_live_rays(const TraceParams &p, uint32_t 
     base = __shfl_sync(0xffffffffu, base, 0);
     if (give) {
         SuspendedRay r;
-        const uint32_t flags = (any ? 1u : 0u) | (found ? 2u : 0u);
+        const uint32_t flags = (any ? kFlagAny : 0u) | (found ? kFlagFound : 0u);
         r.w[0] = make_float4(o[0], o[1], o[2], d[0]);
         r.w[1] = make_float4(d[1], d[2], clip, __uint_as_float(flags));
         r.w[2] = make_float4(hit.t, __uint_as_float(hit.prim), hit.u, hit.v);
@@ -157,7 +174,48 @@ __device__ __forceinline__ void donate_live_rays(const TraceParams &p, uint32_t 
     }
 }
 
-// Helper side: the whole warp resumes the ray in `slot` and writes its result.
+// Called by one lane right after it has made ITS contribution visible (finished++ or served++): if that was the event
+// that made the queue quiescent, announce it.  finished <= started and served <= tail at all times and all four only
+// grow; the counters share one L2 line (one order of events), and served is read before tail, so equality means: when
+// tail was read, every warp that had entered the kernel had left its main loop and nobody was resuming a ray.  Warps
+// that enter later find the work counter exhausted and run through here themselves.
+__device__ __forceinline__ void donate_check_quiescent(const TraceParams &p)
+{
+    __threadfence();
+    const unsigned long long done = ld_volatile_u64(p.counter + kDonateFinished);
+    if (done != ld_volatile_u64(p.counter + kDonateStarted)) {
+        return;
+    }
+    const unsigned long long served = ld_volatile_u64(p.counter + kDonateServed);
+    __threadfence();
+    if (served == ld_volatile_u64(p.counter + kDonateTail)) {
+        *reinterpret_cast<volatile unsigned long long *>(p.counter + kDonateQuiet) = 1ull;
+    }
+}
+
+// The answer of an any-hit ray as far as it is known when its first piece forks: "nothing blocks" / "miss".
+__device__ __forceinline__ void write_optimistic(const TraceParams &p, uint32_t kind, uint64_t out, uint64_t mirror, const float pre[4])
+{
+    if (kind == kFinishVisible) {
+        p.visible[out] = 1;
+        if (mirror != kNoMirror) p.mirror_visible[mirror] = 1;
+    } else { // kFinishAnyRecord
+        const float4 r = make_float4(pre[0], __uint_as_float(DODRT_MISS), 0.0f, 0.0f);
+        reinterpret_cast<float4 *>(p.hits)[out] = r;
+        if (mirror != kNoMirror) reinterpret_cast<float4 *>(p.mirror_hits)[mirror] = r;
+    }
+}
+
+// Has another piece of this (forked, any-hit) ray already found a hit?
+__device__ __forceinline__ bool answer_decided(const TraceParams &p, uint32_t kind, uint64_t out)
+{
+    if (kind == kFinishVisible) {
+        return *reinterpret_cast<const volatile uint8_t *>(p.visible + out) == 0;
+    }
+    return *reinterpret_cast<const volatile uint32_t *>(reinterpret_cast<const uint32_t *>(p.hits + out) + 1) != DODRT_MISS;
+}
+
+// Helper side: the whole warp resumes the ray (or the piece of an any-hit ray) in `slot` and writes its result.
 __device__ __forceinline__ void resume_ray(const TraceParams &p, uint32_t slot)
 {
     const DeviceScene &s = p.scene;
@@ -168,9 +226,10 @@ __device__ __forceinline__ void resume_ray(const TraceParams &p, uint32_t slot)
     const float o[3] = {w0.x, w0.y, w0.z}, d[3] = {w0.w, w1.x, w1.y};
     float clip = w1.z;
     const uint32_t flags = __float_as_uint(w1.w);
-    const bool any = (flags & 1u) != 0u;
-    bool found = (flags & 2u) != 0u;
-    const uint32_t kind = flags >> 2;
+    const bool any = (flags & kFlagAny) != 0u;
+    bool found = (flags & kFlagFound) != 0u;
+    bool forked = (flags & kFlagForked) != 0u;
+    const uint32_t kind = flags >> 3;
     Hit hit;
     hit.t = w2.x, hit.prim = __float_as_uint(w2.y), hit.u = w2.z, hit.v = w2.w;
     const float pre[4] = {w3.x, w3.y, w3.z, w3.w};
@@ -193,6 +252,7 @@ __device__ __forceinline__ void resume_ray(const TraceParams &p, uint32_t slot)
         stackTmin[i] = __uint_as_float(__ldcg(stk + 3 * i + 1));
         stackTmax[i] = __uint_as_float(__ldcg(stk + 3 * i + 2));
     }
+    uint32_t sincePoll = 0;
     while (st.live) { // warp-uniform: every lane holds the same state
         if (st.triCur < st.triEnd) {
             const uint32_t tri = st.triCur + lane;
@@ -230,9 +290,87 @@ __device__ __forceinline__ void resume_ray(const TraceParams &p, uint32_t slot)
         } else {
             node_step(s, st, o, d, clip, stackNode, stackTmin, stackTmax);
         }
+        // ---- work splitting (any-hit rays only): give the oldest stack entries to helpers that wait without a ray
+        if (any && st.live && s.fork_poll != 0u && ++sincePoll >= s.fork_poll) {
+            sincePoll = 0;
+            uint32_t m = 0;
+            bool decided = false;
+            if (lane == 0) {
+                if (forked) {
+                    decided = answer_decided(p, kind, out);
+                }
+                if (!decided && st.sp > 0) {
+                    const unsigned long long head = ld_volatile_u64(p.counter + kDonateHead);
+                    const unsigned long long tail = ld_volatile_u64(p.counter + kDonateTail);
+                    // (same bound as the donors: every warp adds at most 32 slots per check, capacity = 2 x threads)
+                    if (tail <= p.donate_capacity / 2u) {
+                        if (p.scene.tune[3] != 0u) {
+                            m = (uint32_t)st.sp; // DODRT_DONATE_ALWAYS (tests): fork everything, helpers waiting or not
+                        } else if (head > tail) {
+                            const unsigned long long waiting = head - tail;
+                            m = (uint32_t)(waiting < (unsigned long long)st.sp ? waiting : (unsigned long long)st.sp);
+                        }
+                    }
+                }
+            }
+            decided = __shfl_sync(0xffffffffu, decided ? 1 : 0, 0) != 0;
+            m = __shfl_sync(0xffffffffu, m, 0);
+            if (decided) {
+                st.live = false; // a sibling piece found a hit: the OR is true whatever is left here
+                break;
+            }
+            if (m != 0u) {
+                if (!forked) { // first fork of this ray: the optimistic answer goes out before any child can answer
+                    if (lane == 0) {
+                        write_optimistic(p, kind, out, mirror, pre);
+                        __threadfence();
+                    }
+                    forked = true;
+                }
+                unsigned long long base = 0;
+                if (lane == 0) {
+                    if (mirror != kNoMirror) {
+                        __threadfence_system(); // the mirror lives on a peer GPU / in host memory
+                    }
+                    base = atomicAdd(p.counter + kDonateTail, (unsigned long long)m);
+                }
+                base = __shfl_sync(0xffffffffu, base, 0);
+                __syncwarp(); // lane 0's optimistic answer is ordered before any child's publication
+                if (lane < m) { // child `lane` = stack entry `lane` (the oldest entries: the largest sub-trees)
+                    const uint32_t child = (uint32_t)base + lane;
+                    float4 *cw = reinterpret_cast<float4 *>(p.donate_slots + (size_t)child * kDonateSlotWords);
+                    cw[0] = w0;
+                    cw[1] = make_float4(d[1], d[2], clip, __uint_as_float(kFlagAny | kFlagForked | (kind << 3)));
+                    cw[2] = make_float4(clip, __uint_as_float(DODRT_MISS), 0.0f, 0.0f);
+                    cw[3] = w3;
+                    cw[4] = make_float4(stackTmin[lane], stackTmax[lane], __uint_as_float(stackNode[lane]), __uint_as_float(0u));
+                    cw[5] = make_float4(__uint_as_float(0u), __uint_as_float(0u), w5.z, w5.w);
+                    uint32_t *cs = p.donate_slots + (size_t)child * kDonateSlotWords + 24;
+                    cs[kDonateMirrorWord - 24] = (uint32_t)mirror;
+                    cs[kDonateMirrorWord - 24 + 1] = (uint32_t)(mirror >> 32);
+                    __threadfence();
+                    *reinterpret_cast<volatile uint32_t *>(p.donate_ready + child) = p.donate_epoch;
+                }
+                for (int i = 0; i + (int)m < st.sp; i++) { // keep the younger entries
+                    stackNode[i] = stackNode[i + m];
+                    stackTmin[i] = stackTmin[i + m];
+                    stackTmax[i] = stackTmax[i + m];
+                }
+                st.sp -= (int)m;
+            }
+        }
     }
     if (lane == 0) {
-        finish_write(p, kind, out, mirror, found, hit, pre);
+        if (forked) { // pieces of a forked ray only ever turn the optimistic answer into "blocked" / "hit"
+            if (found) {
+                finish_write(p, kind, out, mirror, true, hit, pre);
+            }
+        } else {
+            finish_write(p, kind, out, mirror, found, hit, pre);
+        }
+        __threadfence();
+        atomicAdd(p.counter + kDonateServed, 1ull); // this slot is completely served (see donate_helper_loop)
+        donate_check_quiescent(p);
     }
 }
 
@@ -245,15 +383,20 @@ __device__ __forceinline__ void donate_helper_loop(const TraceParams &p)
     if (lane == 0) {
         __threadfence(); // this warp's donations (if any) are published before it counts as finished
         atomicAdd(p.counter + kDonateFinished, 1ull);
+        donate_check_quiescent(p);
     }
     for (;;) {
         uint32_t ticket = 0;
         if (lane == 0) {
-            ticket = (uint32_t)atomicAdd(p.counter + kDonateHead, 1ull);
+            // enough helpers wait already: this warp would only add polling traffic
+            const unsigned long long head = ld_volatile_u64(p.counter + kDonateHead);
+            const unsigned long long tail = ld_volatile_u64(p.counter + kDonateTail);
+            ticket = (head > tail && head - tail >= p.scene.helper_limit) ? 0xFFFFFFFFu
+                                                                         : (uint32_t)atomicAdd(p.counter + kDonateHead, 1ull);
         }
         ticket = __shfl_sync(0xffffffffu, ticket, 0);
         if (ticket >= p.donate_capacity) {
-            break; // cannot happen while donors respect the capacity bound; never index past the queue
+            break; // over the helper limit, or (cannot happen while donors respect the capacity bound) past the queue
         }
         uint32_t ready = 0;
         if (lane == 0) {
@@ -263,21 +406,16 @@ __device__ __forceinline__ void donate_helper_loop(const TraceParams &p)
                     ready = 1;
                     break;
                 }
-                // "No donor is left" = every warp that ENTERED the kernel has left its main loop.  Warps are counted
-                // when they enter (trace_kernel), not taken from the grid size: blocks that are not resident yet --
-                // the SMs may be shared with another kernel, e.g. a second donating launch on another stream -- must
-                // not be waited for (they could never start while everybody spins here).  A warp that starts later
-                // finds the work counter exhausted (a helper exists only once it is), so it never donates.
-                // finished <= started at all times and both only grow: reading finished first, equal values mean
-                // that all warps started by then had finished by then.
-                const unsigned long long done = ld_volatile_u64(p.counter + kDonateFinished);
-                if (done == ld_volatile_u64(p.counter + kDonateStarted)) {
-                    // slots below tail are filled or being filled by warps that counted as finished only after
-                    // publishing them, so tail is final here
+                // Quiescent (see donate_check_quiescent): no warp is in its main loop -- counted when they ENTER the
+                // kernel, not taken from the grid size: blocks that are not resident yet (the SMs may be shared with
+                // another kernel, e.g. a second donating launch on another stream) must not be waited for -- and no
+                // helper is resuming a ray, so no slot will ever be reserved again: tail is final.
+                if (ld_volatile_u64(p.counter + kDonateQuiet) != 0ull) {
                     __threadfence();
                     if (ld_volatile_u64(p.counter + kDonateTail) <= ticket) {
                         break;
                     }
+                    // tail covers the ticket: the slot was reserved and is being filled
                 }
                 __nanosleep(ns);
                 ns = ns < 3200u ? ns * 2u : ns;

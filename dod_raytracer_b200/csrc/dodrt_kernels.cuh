@@ -71,11 +71,12 @@ struct TraceParams {
 // counters (one 256-B block per launch): [0] next work item, [1]/[2] heavy/light tiles placed (order_tiles_kernel);
 // kModeFrame with tile queues: [3] next shadow item, [4] tiles published in ready_queue;
 // on their own 128-B line, away from the work counter every warp hammers: [16] warps that left the main loop,
-// [17] donation tickets taken by helpers, [18] donation slots reserved by donors, [19] warps that entered the kernel
-// (dodrt_donate.inl)
+// [17] donation tickets taken by helpers, [18] donation slots reserved by donors and forking helpers, [19] warps that
+// entered the kernel, [20] donation slots completely served; [8] set once the queue is quiescent (dodrt_donate.inl)
 constexpr int kCounterWords = 32;
 constexpr int kShadowNext = 3, kReadyTail = 4;
-constexpr int kDonateFinished = 16, kDonateHead = 17, kDonateTail = 18, kDonateStarted = 19;
+constexpr int kDonateFinished = 16, kDonateHead = 17, kDonateTail = 18, kDonateStarted = 19, kDonateServed = 20;
+constexpr int kDonateQuiet = 8; // on the work counter's line, which nobody writes any more once helpers exist
 constexpr int kDonateVariant = 7;
 constexpr int kDonateSlotWords = 80; // 24 header words + 16 stack entries x 3 + mirror index (2) + 6 spare = 320 B
 constexpr int kDonateMirrorWord = 72;

@@ -30,8 +30,9 @@ def main():
         d_vis = torch.empty((1, spr), dtype=torch.uint8, device=dev)
         for r in range(min(nranks, n)):
             f = distributed.rank_frame(w.width, w.height, w.classes, r, n)
-            out = {}
-            for mode in ("fused", "queues", "separate"):
+            modes = os.environ.get("SHARE_MODES", "fused,queues,separate").split(",")
+            out = {m: (float("nan"), float("nan")) for m in ("fused", "queues", "separate")}
+            for mode in modes:
                 os.environ["DODRT_FUSED"] = "0" if mode == "separate" else "1"
                 os.environ["DODRT_FRAME_QUEUES"] = "1" if mode == "queues" else "0"
                 ts = []
