@@ -29,7 +29,7 @@ CLS_ALL = 31
 RAY_ANY = 1
 
 EXPORTED_SYMBOLS = [
-    "dodrt_abi_version", "dodrt_last_error", "dodrt_device_count",
+    "dodrt_abi_version", "dodrt_last_error", "dodrt_device_count", "dodrt_kernel_variant_available",
     "dodrt_scene_create", "dodrt_scene_destroy", "dodrt_scene_set_kdtree", "dodrt_scene_set_kdtree_indexed",
     "dodrt_scene_set_shading_indexed", "dodrt_scene_set_spheres",
     "dodrt_scene_set_planes", "dodrt_scene_set_cylinders", "dodrt_scene_set_boxes", "dodrt_scene_set_epsilon",
@@ -107,6 +107,19 @@ def _ptr(a):
     if isinstance(a, int):
         return C.c_void_p(a)
     return a.ctypes.data_as(C.c_void_p)
+
+
+def variant_available(variant: int) -> bool:
+    """Does the loaded build hold this kernel variant?  (product: 0, 3, 7; libdodrt_cuda_exp.so: 0-8)"""
+    return bool(load().dodrt_kernel_variant_available(C.c_int(variant)))
+
+
+def experiments_build() -> bool:
+    """True for libdodrt_cuda_exp.so (-DDODRT_EXPERIMENTS: A/B variants, one-launch frame kernels, work splitting)."""
+    return variant_available(1)
+
+
+EXP_LIB_PATH = os.path.join(_HERE, "lib", "libdodrt_cuda_exp.so")
 
 
 def device_count() -> int:

@@ -430,7 +430,7 @@ int launchFrameFused(dodrt_scene *s, const dodrt_frame *frame, const float *d_xs
     // A/B knob, read per call: 1 = the one-launch frame kernels.  Default: separate primary / shadow passes, which are
     // faster at every share size (profiles/r02_frame_kernel_ab.txt)
     const char *fusedEnv = std::getenv("DODRT_FUSED");
-    const bool fusedOn = fusedEnv && std::atoi(fusedEnv) != 0;
+    const bool fusedOn = mode_compiled(kModeFrame) && fusedEnv && std::atoi(fusedEnv) != 0;
     if (!fusedOn || numLights > (uint32_t)kMaxLights) return DODRT_OK;
     TraceParams p{};
     p.scene = s->dev;
@@ -557,6 +557,8 @@ extern "C" {
 
 int dodrt_abi_version(void) { return DODRT_ABI_VERSION; }
 
+int dodrt_kernel_variant_available(int variant) { return (variant < 0 || variant_compiled(variant)) ? 1 : 0; }
+
 const char *dodrt_last_error(void) { return g_lastError.c_str(); }
 
 int dodrt_device_count(int *count)
@@ -609,7 +611,7 @@ try {
     s->variant = default_variant();
     for (int v = 0; v < kNumVariants; v++) {
         for (int m = 0; m < kNumModes && e == cudaSuccess; m++) {
-            e = trace_launch_config(device, (TraceMode)m, v, &s->cfg[v][m]);
+            if (variant_compiled(v) && mode_compiled(m)) e = trace_launch_config(device, (TraceMode)m, v, &s->cfg[v][m]);
         }
     }
     if (e != cudaSuccess) {
@@ -968,6 +970,9 @@ int dodrt_scene_set_kernel_variant(dodrt_scene *s, int variant)
 try {
     if (!s) return fail(DODRT_E_INVALID, "scene is NULL");
     if (variant >= kNumVariants) return fail(DODRT_E_INVALID, "kernel variant %d out of range [0,%d)", variant, kNumVariants);
+    if (variant >= 0 && !variant_compiled(variant)) {
+        return fail(DODRT_E_INVALID, "kernel variant %d is an experiment: only in the -DDODRT_EXPERIMENTS build (libdodrt_cuda_exp.so)", variant);
+    }
     std::lock_guard<std::mutex> lock(s->mutex);
     s->variant = variant < 0 ? default_variant() : variant;
     if (s->variant >= 0 && s->variant < 3) return ensureTris(s);

@@ -290,6 +290,7 @@ __device__ __forceinline__ void resume_ray(const TraceParams &p, uint32_t slot)
         } else {
             node_step(s, st, o, d, clip, stackNode, stackTmin, stackTmax);
         }
+#ifdef DODRT_EXPERIMENTS
         // ---- work splitting (any-hit rays only): give the oldest stack entries to helpers that wait without a ray
         if (any && st.live && s.fork_poll != 0u && ++sincePoll >= s.fork_poll) {
             sincePoll = 0;
@@ -359,7 +360,9 @@ __device__ __forceinline__ void resume_ray(const TraceParams &p, uint32_t slot)
                 st.sp -= (int)m;
             }
         }
+#endif // DODRT_EXPERIMENTS (work splitting)
     }
+    (void)sincePoll;
     if (lane == 0) {
         if (forked) { // pieces of a forked ray only ever turn the optimistic answer into "blocked" / "hit"
             if (found) {

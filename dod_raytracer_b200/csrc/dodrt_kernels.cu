@@ -9,7 +9,9 @@
 // query chain (Sphere -> [Box] -> Plane -> Cylinder) and then the kd-tree with a per-thread short stack.
 // The tensor cores are idle by design: the path has no dense contraction.
 //
-// Kernel variants (TraceParams::variant, env DODRT_VARIANT, default = kDefaultVariant):
+// Kernel variants (TraceParams::variant, env DODRT_VARIANT, default = kDefaultVariant).  The product build holds 0 (plain
+// baseline), 3 (default) and 7 (donating); the others were measured slower and are only compiled with -DDODRT_EXPERIMENTS
+// (lib/libdodrt_cuda_exp.so, which the variant parity tests also run), as recorded A/B experiments:
 //   0  per-thread traversal loop, exact reference-order triangle test                (round-1 baseline)
 //   1  same loop, division-deferring triangle test (triangle_test_fast)
 //   2  warp-voted traversal: the warp alternates between "one kd node step" and "one triangle lane
@@ -711,6 +713,7 @@ __global__ void __launch_bounds__(128, VARIANT >= kDonateVariant ? 5 : DODRT_MIN
 }
 
 
+#ifdef DODRT_EXPERIMENTS
 // ---- kModeFrame: primary + shadow rays of a frame share in ONE persistent launch ----------------------------------
 // Two work queues.  Queue 1 holds the primary batches (8x4 pixel blocks, tiles in heavy-first order); queue 2 holds the
 // shadow batches -- still a separate, coherent any-hit pass over 8x4 blocks (main.cpp:182-219 per pixel), but a tile's
@@ -936,8 +939,11 @@ __global__ void __launch_bounds__(128, VARIANT >= kDonateVariant ? 5 : DODRT_MIN
         donate_helper_loop(p);
     }
 }
+#endif // DODRT_EXPERIMENTS (frame kernels)
 
+#ifdef DODRT_EXPERIMENTS
 #include "dodrt_pool_kernel.inl"
+#endif
 
 // One thread per triangle slot: gather the 9 SoA floats of slot j of lane i and emit A, AB, AC.
 // `primNums` (optional) = KDTree::m_primNums: output lane i is source lane primNums[i] -- the reference's
@@ -1026,6 +1032,7 @@ template <int MODE, int VARIANT> cudaError_t config_for(int device, LaunchConfig
     int sms = 0, perSm = 0;
     cudaError_t e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
     if (e != cudaSuccess) return e;
+#ifdef DODRT_EXPERIMENTS
     if constexpr (MODE == kModeFrame) { // the fused kernel exists as the plain voted kernel and as the donating one
         e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, trace_frame_kernel<(VARIANT == kDonateVariant ? kDonateVariant : 3), false>, 128, 0);
         int perSmQ = 0;
@@ -1037,7 +1044,9 @@ template <int MODE, int VARIANT> cudaError_t config_for(int device, LaunchConfig
         e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, trace_kernel_pool<MODE>, 128, 0);
     } else if constexpr (VARIANT == 4) { // the pool kernel has no explicit-ray shadow mode: variant 3 serves it
         e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, trace_kernel<MODE, 3>, 128, 0);
-    } else {
+    } else
+#endif
+    {
         e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, trace_kernel<MODE, VARIANT>, 128, 0);
     }
     if (e != cudaSuccess) return e;
@@ -1049,6 +1058,7 @@ template <int MODE, int VARIANT> cudaError_t config_for(int device, LaunchConfig
 
 template <int MODE, int VARIANT> void launch_one(const TraceParams &p, const LaunchConfig &cfg, cudaStream_t stream)
 {
+#ifdef DODRT_EXPERIMENTS
     if constexpr (MODE == kModeFrame) {
         if (p.tile_done != nullptr) { // tile queues (A/B form, DODRT_FRAME_QUEUES=1)
             trace_frame_kernel<(VARIANT == kDonateVariant ? kDonateVariant : 3), true><<<cfg.grid, cfg.block, 0, stream>>>(p);
@@ -1059,7 +1069,9 @@ template <int MODE, int VARIANT> void launch_one(const TraceParams &p, const Lau
         trace_kernel_pool<MODE><<<cfg.grid, cfg.block, 0, stream>>>(p);
     } else if constexpr (VARIANT == 4) {
         trace_kernel<MODE, 3><<<cfg.grid, cfg.block, 0, stream>>>(p);
-    } else {
+    } else
+#endif
+    {
         trace_kernel<MODE, VARIANT><<<cfg.grid, cfg.block, 0, stream>>>(p);
     }
 }
@@ -1070,7 +1082,11 @@ template <int VARIANT> cudaError_t config_mode(int device, TraceMode mode, Launc
     case kModeRays: return config_for<kModeRays, VARIANT>(device, cfg);
     case kModePrimary: return config_for<kModePrimary, VARIANT>(device, cfg);
     case kModeShadow: return config_for<kModeShadow, VARIANT>(device, cfg);
+#ifdef DODRT_EXPERIMENTS
     case kModeFrame: return config_for<kModeFrame, VARIANT>(device, cfg);
+#else
+    case kModeFrame: return cudaErrorInvalidValue;
+#endif
     default: return config_for<kModeShadowRays, VARIANT>(device, cfg);
     }
 }
@@ -1081,7 +1097,11 @@ template <int VARIANT> void launch_mode(TraceMode mode, const TraceParams &p, co
     case kModeRays: launch_one<kModeRays, VARIANT>(p, cfg, stream); break;
     case kModePrimary: launch_one<kModePrimary, VARIANT>(p, cfg, stream); break;
     case kModeShadow: launch_one<kModeShadow, VARIANT>(p, cfg, stream); break;
+#ifdef DODRT_EXPERIMENTS
     case kModeFrame: launch_one<kModeFrame, VARIANT>(p, cfg, stream); break;
+#else
+    case kModeFrame: break; // not in this build (variant_compiled / mode_compiled are checked by the caller)
+#endif
     default: launch_one<kModeShadowRays, VARIANT>(p, cfg, stream); break;
     }
 }
@@ -1094,7 +1114,7 @@ int default_variant()
         const char *e = std::getenv("DODRT_VARIANT");
         if (!e) return kVariantAuto;
         const int x = std::atoi(e);
-        return (x >= 0 && x < kNumVariants) ? x : kVariantAuto;
+        return variant_compiled(x) ? x : kVariantAuto;
     }();
     return v;
 }
@@ -1120,14 +1140,17 @@ cudaError_t trace_launch_config(int device, TraceMode mode, int variant, LaunchC
 {
     switch (variant) {
     case 0: return config_mode<0>(device, mode, cfg);
+    case 3: return config_mode<3>(device, mode, cfg);
+    case 7: return config_mode<7>(device, mode, cfg);
+#ifdef DODRT_EXPERIMENTS
     case 1: return config_mode<1>(device, mode, cfg);
     case 2: return config_mode<2>(device, mode, cfg);
-    case 3: return config_mode<3>(device, mode, cfg);
     case 4: return config_mode<4>(device, mode, cfg);
     case 5: return config_mode<5>(device, mode, cfg);
     case 6: return config_mode<6>(device, mode, cfg);
-    case 7: return config_mode<7>(device, mode, cfg);
-    default: return config_mode<8>(device, mode, cfg);
+    case 8: return config_mode<8>(device, mode, cfg);
+#endif
+    default: return cudaErrorInvalidValue;
     }
 }
 
@@ -1187,14 +1210,17 @@ cudaError_t launch_trace(TraceMode mode, const TraceParams &params, const Launch
     }
     switch (p.variant) {
     case 0: launch_mode<0>(mode, p, cfg, stream); break;
+    case 3: launch_mode<3>(mode, p, cfg, stream); break;
+    case 7: launch_mode<7>(mode, p, cfg, stream); break;
+#ifdef DODRT_EXPERIMENTS
     case 1: launch_mode<1>(mode, p, cfg, stream); break;
     case 2: launch_mode<2>(mode, p, cfg, stream); break;
-    case 3: launch_mode<3>(mode, p, cfg, stream); break;
     case 4: launch_mode<4>(mode, p, cfg, stream); break;
     case 5: launch_mode<5>(mode, p, cfg, stream); break;
     case 6: launch_mode<6>(mode, p, cfg, stream); break;
-    case 7: launch_mode<7>(mode, p, cfg, stream); break;
-    default: launch_mode<8>(mode, p, cfg, stream); break;
+    case 8: launch_mode<8>(mode, p, cfg, stream); break;
+#endif
+    default: return cudaErrorInvalidValue;
     }
     e = cudaGetLastError();
     if (queue) {

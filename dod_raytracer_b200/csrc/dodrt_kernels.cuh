@@ -16,7 +16,15 @@ constexpr int kNumModes = 5;
 constexpr int kNumVariants = 9;    // see the header comment of dodrt_kernels.cu
 constexpr int kDefaultVariant = 3;
 constexpr int kVariantAuto = -1;   // pick per launch, see resolve_variant
-int default_variant();             // kVariantAuto unless env DODRT_VARIANT names a variant
+int default_variant();             // kVariantAuto unless env DODRT_VARIANT names a (compiled) variant
+#ifdef DODRT_EXPERIMENTS
+constexpr bool kExperiments = true;
+#else
+constexpr bool kExperiments = false;
+#endif
+// the product build instantiates variants 0, 3, 7 and no frame kernels; -DDODRT_EXPERIMENTS adds the rest
+constexpr bool variant_compiled(int v) { return v == 0 || v == 3 || v == 7 || (kExperiments && v >= 0 && v < kNumVariants); }
+constexpr bool mode_compiled(int m) { return m != 4 /* kModeFrame */ || kExperiments; }
 
 struct TraceParams {
     DeviceScene scene;

@@ -164,8 +164,12 @@ DODRT_API int dodrt_scene_set_shading_indexed(dodrt_scene *scene, const void *tr
                                               uint32_t num_meshes, const float *sphere_colors, const float *plane_colors);
 
 /* Tuning / A-B knob: which traversal kernel variant answers the queries (all variants return identical
- * results; see dod_raytracer_b200/csrc/dodrt_kernels.cu).  variant < 0 restores the default. */
+ * results; see dod_raytracer_b200/csrc/dodrt_kernels.cu).  variant < 0 restores the default; a variant this build
+ * does not hold is refused with DODRT_E_INVALID. */
 DODRT_API int dodrt_scene_set_kernel_variant(dodrt_scene *scene, int variant);
+/* 1 if this build of the library holds `variant` (the product build: 0, 3, 7 and "auto" < 0; the -DDODRT_EXPERIMENTS build
+ * libdodrt_cuda_exp.so: all of them, plus the one-launch frame kernels and work splitting in the donation queue) */
+DODRT_API int dodrt_kernel_variant_available(int variant);
 
 /* ---- queries: host buffers (copies in and out are part of the call) --------------------------
  * dodrt_intersect is the batch form of `bool KDTree::intersect(_Intersect&) const` (kdtree.h:13) and

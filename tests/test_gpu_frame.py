@@ -1,7 +1,8 @@
-"""GPU (-m gpu): the one-launch frame path (trace_frame_kernel: primary + shadow queues with per-tile readiness),
-result mirrors (a peer GPU's frame buffer, pinned host memory), frame buffers shared between processes (CUDA IPC) and
-the several-GPUs-one-process API.  Everything must reproduce the bytes of the separate primary / shadow passes, which
-tests/test_gpu_parity.py pins to the oracle, the reference fixtures and the reference itself."""
+"""GPU (-m gpu): dodrt_trace_frame_device (a frame share: primary pass + shadow passes; with libdodrt_cuda_exp.so also
+the one-launch frame kernels, DODRT_FUSED=1), result mirrors (a peer GPU's frame buffer, pinned host memory), frame
+buffers shared between processes (CUDA IPC) and the several-GPUs-one-process API.  Everything must reproduce the bytes of
+the separate primary / shadow entry points, which tests/test_gpu_parity.py pins to the oracle, the reference fixtures and
+the reference itself."""
 import os
 import subprocess
 import sys
@@ -20,8 +21,8 @@ LIGHTS2 = np.stack([LIGHT0, np.array([4.0, 4.3, 3.3], np.float32)])  # lights[0]
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-def _device_frame(g, frame, xs, ys, lights, mirror=None, fused=True):
-    """dodrt_trace_frame_device on torch buffers -> (hits, vis[lights, slots]) as numpy"""
+def _device_frame(g, frame, xs, ys, lights, mirror=None, fused=False):
+    """dodrt_trace_frame_device on torch buffers -> (hits, vis[lights, slots]) as numpy; fused: the A/B frame kernel"""
     import torch
     dev = torch.device("cuda", g.device)
     with torch.cuda.device(dev):
@@ -60,6 +61,8 @@ def _read_frame_buffer(fb, w, h, nl, device=0):
 @pytest.fixture(scope="module", params=[-1, 3, 7, 0], ids=lambda v: f"variant{v}")
 def teapot(request):
     """auto / plain fused / donating fused / a variant without a fused form (falls back to separate passes)"""
+    if not capi.variant_available(request.param):
+        pytest.skip("experiment variant")
     g = upload(teapot_scene(full=True))
     g.set_kernel_variant(request.param)
     g.variant = request.param
@@ -67,6 +70,11 @@ def teapot(request):
     g.close()
 
 
+needs_experiments = pytest.mark.skipif(not capi.experiments_build(), reason="one-launch frame kernels are A/B experiments: "
+                                       "libdodrt_cuda_exp.so only (run by tests/test_gpu_experiments.py)")
+
+
+@needs_experiments
 @pytest.mark.parametrize("w,h,tile", [(640, 360, (32, 32)), (500, 277, (16, 8)), (1920, 1080, (32, 32))])
 def test_fused_launch_equals_separate_passes(teapot, w, h, tile):
     g = teapot
@@ -98,6 +106,11 @@ def test_fused_tile_split_with_frame_buffer_mirror(teapot):
     w, h = 500, 277
     xs, ys = host.ray_tables(w, h)
     full_h, full_v = _device_frame(g, capi.Frame.make(w, h, classes=ALL), xs, ys, LIGHTS2, fused=False)
+    # dodrt_trace_frame_device == the classic entry points (which test_gpu_parity.py pins to the oracle and the reference)
+    ph = g.trace_primary(capi.Frame.make(w, h, classes=ALL), xs, ys)
+    assert ph.tobytes() == full_h.tobytes()
+    for l in range(2):
+        assert g.trace_shadow(capi.Frame.make(w, h, classes=ALL), xs, ys, ph, LIGHTS2[l]).tobytes() == full_v[l].tobytes()
     for world, tile in ((2, (32, 32)), (5, (16, 8))):
         with capi.FrameBuffer.create(g, w, h, 2) as fb:
             hits0, vis0 = _read_frame_buffer(fb, w, h, 2)
@@ -106,7 +119,8 @@ def test_fused_tile_split_with_frame_buffer_mirror(teapot):
                 f = capi.Frame.make(w, h, classes=ALL, tile=tile, first_tile=rank, tile_stride=world, compact=1)
                 m = capi.frame_pixel_map(f)
                 ok = m != 0xFFFFFFFF
-                lh, lv = _device_frame(g, f, xs, ys, LIGHTS2, mirror=fb)
+                # (the experiments build alternates between the product path and the one-launch frame kernel)
+                lh, lv = _device_frame(g, f, xs, ys, LIGHTS2, mirror=fb, fused=capi.experiments_build() and rank % 2 == 1)
                 assert lh[ok].tobytes() == full_h[m[ok]].tobytes() and (lh["prim"][~ok] == MISS).all()
                 assert lv[:, ok].tobytes() == full_v[:, m[ok]].tobytes() and not lv[:, ~ok].any()
             hits, vis = _read_frame_buffer(fb, w, h, 2)
