@@ -37,7 +37,7 @@ import numpy as np  # noqa: E402
 
 METRIC = "Mrays/s (primary+shadow)"
 UNIT = "Mrays/s"
-FRAME_KERNEL = "trace_frame_kernel"
+FRAME_KERNEL = "frame share (primary + shadow passes)"
 
 
 def parse_args():
@@ -48,7 +48,7 @@ def parse_args():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="dragon4k")
     ap.add_argument("--tile", default="32x32")
-    ap.add_argument("--separate", action="store_true", help="A/B: separate primary / shadow launches instead of the one-launch frame kernel")
+    ap.add_argument("--separate", action="store_true", help="N > 1: issue the passes one by one (per-pass event times) instead of dodrt_trace_frame_device")
     ap.add_argument("--gather", default="peer", choices=["peer", "nccl"],
                     help="N > 1: ranks store into rank 0's frame over NVLink (peer) or NCCL gather + assembly kernel (A/B, fallback)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -307,8 +307,6 @@ def main():
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    if args.separate:
-        os.environ["DODRT_FUSED"] = "0"
     tmpdir = tempfile.mkdtemp(prefix=f"dodrt_bench_{rank}_")
     mesh_files = workloads.write_mesh_files(w, tmpdir)
     t0 = time.perf_counter()
@@ -380,7 +378,9 @@ def main():
     stream = torch.cuda.current_stream()
     side = torch.cuda.Stream(device=dev) if (world > 1 and gather == "nccl") else None  # carries the hit-record gather
     hits_ready, hits_gathered = torch.cuda.Event(), torch.cuda.Event()
-    two_pass = args.separate or (world > 1 and gather == "nccl")
+    # N = 1: the two passes of dodrt_trace_frame_device are issued one by one here so that CUDA events can time each
+    # kernel on its own (same kernels, same order); N > 1: the one call a rank makes, results mirrored into rank 0's frame
+    two_pass = world == 1 or args.separate or gather == "nccl"
 
     def step(ev=None):
         sp = stream.cuda_stream
@@ -561,10 +561,11 @@ def main():
             reference_frame = {"error": repr(exc)}
 
     if world == 1:
-        how = "one launch per frame (trace_frame_kernel)" if not two_pass else "separate primary / shadow launches (A/B)"
+        how = "primary pass + one coherent shadow pass per light (persistent kernels, warp-voted traversal)"
     elif gather == "peer":
-        how = (f"image tiles round-robin over {world} GPUs, scene replicated; one launch per rank, every result stored straight into "
-               "rank 0's row-major frame buffer over NVLink by the kernel (CUDA IPC peer mapping); no gather, no assembly pass")
+        how = (f"image tiles round-robin over {world} GPUs, scene replicated; dodrt_trace_frame_device per rank (primary + shadow "
+               "pass, donating kernels), every result stored straight into rank 0's row-major frame buffer over NVLink by the "
+               "kernels themselves (CUDA IPC peer mapping); no gather, no assembly pass")
     else:
         how = (f"image tiles round-robin over {world} GPUs, scene replicated; NCCL gather to rank 0 overlapped with the shadow pass + "
                "dodrt_frame_assemble_device")
