@@ -29,7 +29,7 @@ CLS_ALL = 31
 RAY_ANY = 1
 
 EXPORTED_SYMBOLS = [
-    "dodrt_abi_version", "dodrt_last_error", "dodrt_device_count", "dodrt_kernel_variant_available",
+    "dodrt_abi_version", "dodrt_last_error", "dodrt_device_count", "dodrt_kernel_variant_available", "dodrt_scene_debug_stats",
     "dodrt_scene_create", "dodrt_scene_destroy", "dodrt_scene_set_kdtree", "dodrt_scene_set_kdtree_indexed",
     "dodrt_scene_set_shading_indexed", "dodrt_scene_set_spheres",
     "dodrt_scene_set_planes", "dodrt_scene_set_cylinders", "dodrt_scene_set_boxes", "dodrt_scene_set_epsilon",
@@ -39,7 +39,7 @@ EXPORTED_SYMBOLS = [
     "dodrt_frame_assemble_device", "dodrt_frame_local_pixels", "dodrt_frame_pixel_map", "dodrt_scene_launch_count",
     "dodrt_trace_frame_device", "dodrt_frame_buffer_create", "dodrt_frame_buffer_export", "dodrt_frame_buffer_open",
     "dodrt_frame_buffer_attach", "dodrt_frame_buffer_pointers", "dodrt_frame_buffer_destroy",
-    "dodrt_multi_create", "dodrt_multi_trace_frame", "dodrt_multi_destroy",
+    "dodrt_multi_create", "dodrt_multi_trace_frame", "dodrt_multi_render", "dodrt_multi_destroy",
 ]
 ABI_VERSION = 2
 
@@ -209,7 +209,12 @@ class Scene:
         """dodrt_render: the reference's rayTrace for the whole frame; lights = [[x, y, z, intensity], ...]."""
         xs, ys = np.ascontiguousarray(xs, np.float32), np.ascontiguousarray(ys, np.float32)
         lights = np.ascontiguousarray(lights, np.float32).reshape(-1, 4)
-        rgb = out if out is not None else np.empty((frame.height, frame.width, 3), np.uint8)
+        if out is not None:
+            rgb = out
+        elif frame.compact:
+            rgb = np.empty((frame_local_pixels(frame), 3), np.uint8)
+        else:
+            rgb = np.empty((frame.height, frame.width, 3), np.uint8)
         _check(self._lib.dodrt_render(self._h, C.byref(frame), _ptr(xs), _ptr(ys), _ptr(lights), C.c_uint32(len(lights)),
                                       C.c_uint32(depth), _ptr(rgb)))
         return rgb
@@ -290,6 +295,12 @@ class Scene:
                                                   C.c_uint32(len(lights)), C.c_void_p(d_hits),
                                                   C.c_void_p(d_visible) if d_visible else None,
                                                   mirror._h if mirror is not None else None, C.c_void_p(stream)))
+
+    def debug_stats(self, enable: bool) -> np.ndarray:
+        """dodrt_scene_debug_stats: counters since the last call (see include/dodrt.h), then on / off."""
+        out = np.zeros(8, np.uint64)
+        _check(self._lib.dodrt_scene_debug_stats(self._h, C.c_int(1 if enable else 0), _ptr(out)))
+        return out
 
     def launch_count(self) -> int:
         n = C.c_uint64(0)
@@ -388,6 +399,15 @@ class Multi:
         _check(self._lib.dodrt_multi_trace_frame(self._h, C.byref(frame), _ptr(xs), _ptr(ys), _ptr(lights),
                                                  C.c_uint32(len(lights)), _ptr(hits), _ptr(vis)))
         return hits, vis
+
+    def render(self, frame: Frame, xs, ys, lights, depth: int = 10, out: Optional[np.ndarray] = None) -> np.ndarray:
+        """dodrt_multi_render: the reference's rayTrace for the whole frame on all GPUs, one row-major rgb image."""
+        xs, ys = np.ascontiguousarray(xs, np.float32), np.ascontiguousarray(ys, np.float32)
+        lights = np.ascontiguousarray(lights, np.float32).reshape(-1, 4)
+        rgb = out if out is not None else np.empty((frame.height, frame.width, 3), np.uint8)
+        _check(self._lib.dodrt_multi_render(self._h, C.byref(frame), _ptr(xs), _ptr(ys), _ptr(lights), C.c_uint32(len(lights)),
+                                            C.c_uint32(depth), _ptr(rgb)))
+        return rgb
 
     def close(self):
         if getattr(self, "_h", None) is not None and self._h:

@@ -107,6 +107,7 @@ struct dodrt_scene {
     uint32_t *d_triAttrs = nullptr;
     float *d_meshColors = nullptr, *d_sphereColors = nullptr, *d_planeColors = nullptr;
     unsigned long long *d_counters = nullptr;
+    unsigned long long *d_stats = nullptr; // dodrt_scene_debug_stats
     std::atomic<uint32_t> nextCounter{0};
     std::atomic<uint64_t> launches{0};
     LaunchConfig cfg[kNumVariants][kNumModes]{};
@@ -656,6 +657,7 @@ try {
     freeDevice(s->d_sphereColors);
     freeDevice(s->d_planeColors);
     freeDevice(s->d_counters);
+    freeDevice(s->d_stats);
     delete s;
     return DODRT_OK;
 }
@@ -1601,46 +1603,39 @@ DODRT_CATCH
 
 // ---- shading + bounce loop ----------------------------------------------------------------
 
-int dodrt_render(dodrt_scene *s, const dodrt_frame *frame, const float *xs, const float *ys, const float *lights,
-                 uint32_t num_lights, uint32_t depth, uint8_t *rgb)
-try {
-    if (!s) return fail(DODRT_E_INVALID, "scene is NULL");
-    int rc = checkFrame(frame);
-    if (rc != DODRT_OK) return rc;
-    if (!xs || !ys || !rgb || (num_lights && !lights)) return fail(DODRT_E_INVALID, "NULL argument");
-    if (num_lights > (uint32_t)kMaxLights) return fail(DODRT_E_LIMIT, "%u lights exceed the limit of %d", num_lights, kMaxLights);
-    if ((s->dev.num_tri_lanes && !s->dev.tri_attrs) || (s->dev.num_spheres && !s->dev.sphere_colors) ||
-        (s->dev.num_planes && !s->dev.plane_colors)) {
-        return fail(DODRT_E_INVALID, "dodrt_scene_set_shading has not been called for this scene");
-    }
-    rc = ensureStream(s);
-    if (rc != DODRT_OK) return rc;
-    DeviceGuard guard(s->device);
-    if (!guard.ok) return fail(DODRT_E_CUDA, "cannot select device %d", s->device);
+// rayTrace (main.cpp:273-347) for the call's tiles, asynchronous on the scene's stream.  `d_rgb`: where the finish kernel
+// stores the 8-bit pixels (by pixel: any memory this GPU can write -- local, a peer GPU's, pinned host; by slot: local).
+// The working arrays come from the scene's pool and are released on the stream.
+static int renderOnDevice(dodrt_scene *s, const dodrt_frame *frame, const float *xs, const float *ys, const float *lights,
+                          uint32_t num_lights, uint32_t depth, uint8_t *d_rgb, bool rgbByPixel)
+{
     cudaStream_t st = s->stream;
-    const uint64_t n = (uint64_t)frame->width * frame->height;
-    float *d_tables = nullptr;
     RenderParams rp{};
     rp.scene = s->dev;
-    rp.width = frame->width;
-    rp.height = frame->height;
-    for (int k = 0; k < 3; k++) rp.origin[k] = frame->origin[k];
+    rp.frame = *frame;
+    uint32_t tiles;
+    frameTiles(frame, &rp.tiles_x, &tiles);
+    const uint64_t n = (uint64_t)tiles * frame->tile_w * frame->tile_h;
+    rp.slots = n;
+    if (n == 0) return DODRT_OK;
     rp.num_lights = num_lights;
     for (uint32_t l = 0; l < num_lights; l++) {
         for (int k = 0; k < 4; k++) rp.lights[l][k] = lights[l * 4 + k];
     }
+    float *d_tables = nullptr;
     cudaError_t e = cudaMallocFromPoolAsync(&d_tables, ((size_t)frame->width + frame->height) * sizeof(float), s->pool, st);
     if (e == cudaSuccess) e = cudaMallocFromPoolAsync(&rp.rays, n * sizeof(dodrt_ray), s->pool, st);
     if (e == cudaSuccess) e = cudaMallocFromPoolAsync(&rp.hits, n * sizeof(dodrt_hit), s->pool, st);
     if (e == cudaSuccess) e = cudaMallocFromPoolAsync(&rp.visible, n * (num_lights ? num_lights : 1), s->pool, st);
     if (e == cudaSuccess) e = cudaMallocFromPoolAsync(&rp.accum, n * sizeof(float4), s->pool, st);
-    if (e == cudaSuccess) e = cudaMallocFromPoolAsync(&rp.rgb, n * 3, s->pool, st);
     if (e == cudaSuccess) e = cudaMemcpyAsync(d_tables, xs, frame->width * sizeof(float), cudaMemcpyHostToDevice, st);
     if (e == cudaSuccess) {
         e = cudaMemcpyAsync(d_tables + frame->width, ys, frame->height * sizeof(float), cudaMemcpyHostToDevice, st);
     }
     rp.xs = d_tables;
     rp.ys = d_tables ? d_tables + frame->width : nullptr;
+    rp.rgb = d_rgb;
+    rp.rgb_by_pixel = rgbByPixel ? 1u : 0u;
     if (e == cudaSuccess) e = launch_render_init(rp, st);
     if (e == cudaSuccess) s->launches.fetch_add(1);
     for (uint32_t k = 0; k < depth && e == cudaSuccess; k++) { // main.cpp:312
@@ -1655,10 +1650,17 @@ try {
         p.counter = nextCounter(s);
         e = launchTraceOn(s, kModeRays, p, st); // closest-hit chain, main.cpp:314-321
         if (e == cudaSuccess) s->launches.fetch_add(1);
-        for (uint32_t l = 0; l < num_lights && e == cudaSuccess; l++) { // canSeeLight per light, main.cpp:226
+        if (num_lights && e == cudaSuccess) { // canSeeLight for every light (main.cpp:226): one launch, light-major
             p.counter = nextCounter(s);
-            p.visible = rp.visible + n * l;
-            for (int c = 0; c < 3; c++) p.light[c] = rp.lights[l][c];
+            p.visible = rp.visible;
+            p.num_lights = num_lights;
+            p.rays_per_light = n;
+            p.count = n * num_lights;
+            for (uint32_t l = 0; l < num_lights; l++) {
+                for (int c = 0; c < 3; c++) p.lights[l][c] = rp.lights[l][c];
+            }
+            for (int c = 0; c < 3; c++) p.light[c] = rp.lights[0][c];
+            p.variant = resolve_variant(s->variant, s->cfg[kDonateVariant][kModeShadowRays], p.count, true, s->dev.num_nodes >= kBigTreeNodes);
             e = launchTraceOn(s, kModeShadowRays, p, st);
             if (e == cudaSuccess) s->launches.fetch_add(1);
         }
@@ -1667,16 +1669,124 @@ try {
     }
     if (e == cudaSuccess) e = launch_render_finish(rp, st);
     if (e == cudaSuccess) s->launches.fetch_add(1);
-    if (e == cudaSuccess) e = cudaMemcpyAsync(rgb, rp.rgb, n * 3, cudaMemcpyDeviceToHost, st);
     if (d_tables) cudaFreeAsync(d_tables, st);
     if (rp.rays) cudaFreeAsync(rp.rays, st);
     if (rp.hits) cudaFreeAsync(rp.hits, st);
     if (rp.visible) cudaFreeAsync(rp.visible, st);
     if (rp.accum) cudaFreeAsync(rp.accum, st);
-    if (rp.rgb) cudaFreeAsync(rp.rgb, st);
+    if (e != cudaSuccess) return fail(DODRT_E_CUDA, "dodrt_render: %s", cudaGetErrorString(e));
+    return DODRT_OK;
+}
+
+static int checkRender(dodrt_scene *s, const dodrt_frame *frame, const float *xs, const float *ys, const float *lights,
+                       uint32_t num_lights, const uint8_t *rgb)
+{
+    if (!s) return fail(DODRT_E_INVALID, "scene is NULL");
+    int rc = checkFrame(frame);
+    if (rc != DODRT_OK) return rc;
+    if (!xs || !ys || !rgb || (num_lights && !lights)) return fail(DODRT_E_INVALID, "NULL argument");
+    if (num_lights > (uint32_t)kMaxLights) return fail(DODRT_E_LIMIT, "%u lights exceed the limit of %d", num_lights, kMaxLights);
+    if ((s->dev.num_tri_lanes && !s->dev.tri_attrs) || (s->dev.num_spheres && !s->dev.sphere_colors) ||
+        (s->dev.num_planes && !s->dev.plane_colors)) {
+        return fail(DODRT_E_INVALID, "dodrt_scene_set_shading has not been called for this scene");
+    }
+    return DODRT_OK;
+}
+
+int dodrt_render(dodrt_scene *s, const dodrt_frame *frame, const float *xs, const float *ys, const float *lights,
+                 uint32_t num_lights, uint32_t depth, uint8_t *rgb)
+try {
+    int rc = checkRender(s, frame, xs, ys, lights, num_lights, rgb);
+    if (rc != DODRT_OK) return rc;
+    rc = ensureStream(s);
+    if (rc != DODRT_OK) return rc;
+    DeviceGuard guard(s->device);
+    if (!guard.ok) return fail(DODRT_E_CUDA, "cannot select device %d", s->device);
+    std::lock_guard<std::mutex> hostLock(s->hostMutex);
+    cudaStream_t st = s->stream;
+    const bool byPixel = !frame->compact;
+    const uint64_t outPixels = byPixel ? (uint64_t)frame->width * frame->height : frameSlots(frame);
+    if (outPixels == 0) return DODRT_OK;
+    uint8_t *d_rgb = nullptr;
+    CUDA_TRY(cudaMallocFromPoolAsync(&d_rgb, outPixels * 3, s->pool, st));
+    cudaError_t e = cudaSuccess;
+    if (byPixel && frame->tile_stride > 1) e = cudaMemsetAsync(d_rgb, 0, outPixels * 3, st); // other ranks' pixels read as black
+    if (e == cudaSuccess) rc = renderOnDevice(s, frame, xs, ys, lights, num_lights, depth, d_rgb, byPixel);
+    if (e == cudaSuccess && rc == DODRT_OK) e = cudaMemcpyAsync(rgb, d_rgb, outPixels * 3, cudaMemcpyDeviceToHost, st);
+    cudaFreeAsync(d_rgb, st);
     cudaError_t es = cudaStreamSynchronize(st);
+    if (rc != DODRT_OK) return rc;
     if (e == cudaSuccess) e = es;
     if (e != cudaSuccess) return fail(DODRT_E_CUDA, "dodrt_render: %s", cudaGetErrorString(e));
+    return DODRT_OK;
+}
+DODRT_CATCH
+
+// The reference renders the frame with all the threads of the process (one row band each, main.cpp:371-394); this renders
+// it with all the GPUs of the process: tiles dealt round-robin, every GPU's finish kernel stores its pixels straight into
+// the ONE rgb frame -- the caller's pinned host buffer, or (pageable host memory) a frame in scenes[0]'s HBM over peer
+// stores, copied out once.
+int dodrt_multi_render(dodrt_multi *m, const dodrt_frame *frame, const float *xs, const float *ys, const float *lights,
+                       uint32_t num_lights, uint32_t depth, uint8_t *rgb)
+try {
+    if (!m) return fail(DODRT_E_INVALID, "multi is NULL");
+    std::lock_guard<std::mutex> lock(m->mutex);
+    const uint32_t n = (uint32_t)m->scenes.size();
+    for (uint32_t i = 0; i < n; i++) {
+        int rc = checkRender(m->scenes[i], frame, xs, ys, lights, num_lights, rgb);
+        if (rc != DODRT_OK) return rc;
+    }
+    const uint64_t bytes = (uint64_t)frame->width * frame->height * 3;
+    uint8_t *dest = nullptr, *d_frame = nullptr;
+    {
+        DeviceGuard guard(m->scenes[0]->device);
+        dest = static_cast<uint8_t *>(mappedHostPointer(rgb, bytes));
+        if (!dest) { // pageable: assemble in scenes[0]'s HBM (peer access as for the frame buffers)
+            CUDA_TRY(cudaMalloc(&d_frame, bytes));
+            dest = d_frame;
+        }
+    }
+    int rc = DODRT_OK;
+    uint32_t launched = 0;
+    for (uint32_t i = 0; i < n && rc == DODRT_OK; i++) {
+        dodrt_scene *s = m->scenes[i];
+        DeviceGuard guard(s->device);
+        if (!guard.ok) {
+            rc = fail(DODRT_E_CUDA, "cannot select device %d", s->device);
+            break;
+        }
+        if (d_frame && s->device != m->scenes[0]->device) {
+            cudaError_t pe = cudaDeviceEnablePeerAccess(m->scenes[0]->device, 0);
+            if (pe == cudaErrorPeerAccessAlreadyEnabled) {
+                cudaGetLastError();
+            } else if (pe != cudaSuccess) {
+                rc = fail(DODRT_E_CUDA, "cudaDeviceEnablePeerAccess(%d -> %d): %s", s->device, m->scenes[0]->device, cudaGetErrorString(pe));
+                break;
+            }
+        }
+        s->hostMutex.lock();
+        launched = i + 1;
+        dodrt_frame f = *frame;
+        f.first_tile = i;
+        f.tile_stride = n;
+        f.compact = 0;
+        rc = renderOnDevice(s, &f, xs, ys, lights, num_lights, depth, dest, true);
+    }
+    cudaError_t e = cudaSuccess;
+    for (uint32_t i = 0; i < launched; i++) {
+        dodrt_scene *s = m->scenes[i];
+        DeviceGuard guard(s->device);
+        cudaError_t es = cudaStreamSynchronize(s->stream);
+        if (e == cudaSuccess) e = es;
+        s->hostMutex.unlock();
+    }
+    if (d_frame) {
+        DeviceGuard guard(m->scenes[0]->device);
+        if (rc == DODRT_OK && e == cudaSuccess) e = cudaMemcpy(rgb, d_frame, bytes, cudaMemcpyDeviceToHost);
+        cudaFree(d_frame);
+    }
+    if (rc != DODRT_OK) return rc;
+    if (e != cudaSuccess) return fail(DODRT_E_CUDA, "dodrt_multi_render: %s", cudaGetErrorString(e));
     return DODRT_OK;
 }
 DODRT_CATCH
@@ -1712,6 +1822,24 @@ try {
         const uint32_t row = ty * f->tile_h + (block / bpr) * 4 + (lane >> 3);
         pixel_of_slot[slot] = (col < f->width && row < f->height) ? row * f->width + col : 0xFFFFFFFFu;
     }
+    return DODRT_OK;
+}
+DODRT_CATCH
+
+int dodrt_scene_debug_stats(dodrt_scene *s, int enable, uint64_t out[8])
+try {
+    if (!s) return fail(DODRT_E_INVALID, "scene is NULL");
+    std::lock_guard<std::mutex> lock(s->mutex);
+    DeviceGuard guard(s->device);
+    if (!guard.ok) return fail(DODRT_E_CUDA, "cannot select device %d", s->device);
+    CUDA_TRY(cudaDeviceSynchronize());
+    if (out) {
+        std::memset(out, 0, 8 * sizeof(uint64_t));
+        if (s->d_stats) CUDA_TRY(cudaMemcpy(out, s->d_stats, 8 * sizeof(uint64_t), cudaMemcpyDeviceToHost));
+    }
+    if (enable && !s->d_stats) CUDA_TRY(cudaMalloc(&s->d_stats, 8 * sizeof(unsigned long long)));
+    if (s->d_stats) CUDA_TRY(cudaMemset(s->d_stats, 0, 8 * sizeof(unsigned long long)));
+    s->dev.stats = enable ? s->d_stats : nullptr;
     return DODRT_OK;
 }
 DODRT_CATCH

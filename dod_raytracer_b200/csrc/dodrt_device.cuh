@@ -65,6 +65,9 @@ struct DeviceScene {
     uint32_t donate_poll;
     // variant 4: idle lanes that send the warp back to top up its ray pool (32 = only when every ray is finished)
     uint32_t pool_refill;
+    // instrumentation (dodrt_scene_debug_stats, nullptr = off): [0]/[1] culling-BVH nodes fetched / primitives tested for
+    // spheres, [2]/[3] the same for boxes, [4] rays that took a culling BVH
+    unsigned long long *stats;
     // variant 7: resume steps between two fork polls of a resumed any-hit ray (0 = no work splitting), and how many
     // helpers may wait for a ray at a time (further idle warps leave the kernel)
     uint32_t fork_poll;
@@ -686,6 +689,30 @@ __device__ __forceinline__ bool box_query(const DeviceScene &s, const float o[3]
     hit.prim = (DODRT_KIND_BOX << DODRT_KIND_SHIFT) | closest;
     hit.u = hit.v = 0.0f;
     return true;
+}
+
+// work item -> pixel for the frame modes (see dodrt_frame in include/dodrt.h): tiles round-robin over
+// ranks, 8x4 pixel blocks inside a tile so that one warp = one block.  `order` (optional) is the order in which
+// the call's local tiles are PROCESSED; `slot` is where the item's result goes in a compact buffer and does
+// not depend on it.
+__device__ __forceinline__ bool slot_to_pixel(const dodrt_frame &f, uint32_t tiles_x, const uint32_t *order, uint64_t item,
+                                              uint32_t &col, uint32_t &row, uint64_t &slot)
+{
+    const uint32_t tilePixels = f.tile_w * f.tile_h;
+    uint32_t localTile = (uint32_t)(item / tilePixels);
+    const uint32_t in = (uint32_t)(item % tilePixels);
+    if (order) {
+        localTile = __ldg(order + localTile);
+    }
+    slot = (uint64_t)localTile * tilePixels + in;
+    const uint32_t tile = f.first_tile + localTile * f.tile_stride;
+    const uint32_t tx = tile % tiles_x, ty = tile / tiles_x;
+    const uint32_t block = in >> 5, lane = in & 31u;
+    const uint32_t bpr = f.tile_w >> 3;
+    const uint32_t bx = block % bpr, by = block / bpr;
+    col = tx * f.tile_w + bx * 8 + (lane & 7u);
+    row = ty * f.tile_h + by * 4 + (lane >> 3);
+    return col < f.width && row < f.height;
 }
 
 // Primary ray direction, main.cpp:304: glm::normalize(v) = v * (1 / sqrt(dot(v,v)))

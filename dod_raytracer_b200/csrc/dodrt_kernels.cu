@@ -408,7 +408,7 @@ __device__ __forceinline__ bool analytic_chain(const DeviceScene &s, uint32_t cl
     // dodrt_ray.d need not be normalised, so any other ray takes the reference's own loop over every lane.
     const bool unitDir = fabsf(dot3(d[0], d[1], d[2], d[0], d[1], d[2]) - 1.0f) <= 2e-6f;
     if ((classes & DODRT_CLS_SPHERE) && s.num_spheres &&
-        ((s.sphere_bvh && unitDir) ? prim_bvh_query<DODRT_KIND_SPHERE>(s.sphere_bvh, s.sphere_bvh_ids, s.sphere_lanes, o, d, any, clip, h)
+        ((s.sphere_bvh && unitDir) ? prim_bvh_query<DODRT_KIND_SPHERE>(s.sphere_bvh, s.sphere_bvh_ids, s.sphere_lanes, o, d, any, clip, h, s.stats)
                                    : sphere_query(s, o, d, any, clip, h))) {
         hit = h;
         found = true;
@@ -416,7 +416,7 @@ __device__ __forceinline__ bool analytic_chain(const DeviceScene &s, uint32_t cl
         clip = h.t;
     }
     if ((classes & DODRT_CLS_BOX) && s.num_boxes &&
-        ((s.box_bvh && unitDir) ? prim_bvh_query<DODRT_KIND_BOX>(s.box_bvh, s.box_bvh_ids, s.box_lanes, o, d, any, clip, h)
+        ((s.box_bvh && unitDir) ? prim_bvh_query<DODRT_KIND_BOX>(s.box_bvh, s.box_bvh_ids, s.box_lanes, o, d, any, clip, h, s.stats)
                                 : box_query(s, o, d, any, clip, h))) {
         hit = h;
         found = true;
@@ -483,30 +483,6 @@ __device__ __forceinline__ bool query(const DeviceScene &s, uint32_t classes, bo
         found = true;
     }
     return found;
-}
-
-// work item -> pixel for the frame modes (see dodrt_frame in include/dodrt.h): tiles round-robin over
-// ranks, 8x4 pixel blocks inside a tile so that one warp = one block.  `order` (optional) is the order in which
-// the call's local tiles are PROCESSED; `slot` is where the item's result goes in a compact buffer and does
-// not depend on it.
-__device__ __forceinline__ bool slot_to_pixel(const dodrt_frame &f, uint32_t tiles_x, const uint32_t *order, uint64_t item,
-                                              uint32_t &col, uint32_t &row, uint64_t &slot)
-{
-    const uint32_t tilePixels = f.tile_w * f.tile_h;
-    uint32_t localTile = (uint32_t)(item / tilePixels);
-    const uint32_t in = (uint32_t)(item % tilePixels);
-    if (order) {
-        localTile = __ldg(order + localTile);
-    }
-    slot = (uint64_t)localTile * tilePixels + in;
-    const uint32_t tile = f.first_tile + localTile * f.tile_stride;
-    const uint32_t tx = tile % tiles_x, ty = tile / tiles_x;
-    const uint32_t block = in >> 5, lane = in & 31u;
-    const uint32_t bpr = f.tile_w >> 3;
-    const uint32_t bx = block % bpr, by = block / bpr;
-    col = tx * f.tile_w + bx * 8 + (lane & 7u);
-    row = ty * f.tile_h + by * 4 + (lane >> 3);
-    return col < f.width && row < f.height;
 }
 
 // Heavy-first tile order.  A persistent kernel ends when its slowest warp ends, and a 32-ray batch that grazes
@@ -599,12 +575,20 @@ __global__ void __launch_bounds__(128, VARIANT >= kDonateVariant ? 5 : DODRT_MIN
             float so[3] = {0.0f, 0.0f, 0.0f}, sd[3] = {0.0f, 0.0f, 1.0f}, sclip = 0.0f;
             bool cast = false;
             if (inRange) {
-                const float4 *src = reinterpret_cast<const float4 *>(p.rays + item);
+                // all lights of a bounce in one launch: item = light * rays_per_light + ray
+                uint64_t ray = item;
+                float light3[3] = {p.light[0], p.light[1], p.light[2]};
+                if (p.num_lights > 1u) {
+                    const uint32_t l = (uint32_t)(item / p.rays_per_light);
+                    ray = item - (uint64_t)l * p.rays_per_light;
+                    light3[0] = p.lights[l][0], light3[1] = p.lights[l][1], light3[2] = p.lights[l][2];
+                }
+                const float4 *src = reinterpret_cast<const float4 *>(p.rays + ray);
                 const float4 a = src[0], b = src[1];
-                const float4 ph = reinterpret_cast<const float4 *>(p.hits)[item];
+                const float4 ph = reinterpret_cast<const float4 *>(p.hits)[ray];
                 if (!(__float_as_uint(b.w) & DODRT_RAY_SKIP) && __float_as_uint(ph.y) != DODRT_MISS) {
                     const float o[3] = {a.x, a.y, a.z}, d[3] = {a.w, b.x, b.y};
-                    shadow_ray(o, d, ph.x, p.light, so, sd, sclip);
+                    shadow_ray(o, d, ph.x, light3, so, sd, sclip);
                     cast = true;
                 }
             }

@@ -68,8 +68,11 @@ struct TraceParams {
     // makes a tile's shadow batches claimable once its primary records are complete (all zeroed before the launch):
     // tile_done[t] = primary batches of local tile t finished; ready_queue[k] = 1 + the k-th tile that became complete.
     // nullptr = the block-fused form of the frame kernel (no queues at all)
+    // kModeShadowRays with num_lights > 1: ONE launch for all lights of a bounce (item = light * rays_per_light + ray,
+    // which is also its index in `visible`)
     uint32_t num_lights;
     float lights[16][3];
+    uint64_t rays_per_light;
     uint64_t visible_light_stride;
     uint64_t shadow_count; // count * num_lights
     uint32_t *tile_done;
@@ -111,14 +114,20 @@ cudaError_t launch_trace(TraceMode mode, const TraceParams &p, const LaunchConfi
 constexpr int kMaxLights = 16;
 struct RenderParams {
     DeviceScene scene;
-    uint32_t width, height;
-    float origin[3];
+    // the call's share of the image: result slots of `frame` (tiles first_tile, first_tile + tile_stride, ..., 8x4 pixel
+    // blocks inside a tile; padded slots of edge tiles carry DODRT_RAY_SKIP rays).  All per-pixel arrays are indexed by slot.
+    dodrt_frame frame;
+    uint32_t tiles_x;
+    uint64_t slots;
     const float *xs, *ys;
-    dodrt_ray *rays;     // current ray of every pixel
+    dodrt_ray *rays;     // current ray of every slot
     dodrt_hit *hits;     // its closest hit
-    uint8_t *visible;    // [num_lights][pixels] canSeeLight results of this bounce
+    uint8_t *visible;    // [num_lights][slots] canSeeLight results of this bounce
     float4 *accum;       // finalColor
-    uint8_t *rgb;        // output, 3 bytes per pixel
+    // output, 3 bytes per pixel: indexed by pixel (row * width + col; local, a peer GPU's or pinned host memory -- the
+    // kernel stores straight into it) when rgb_by_pixel, else by slot (padded slots zero)
+    uint8_t *rgb;
+    uint32_t rgb_by_pixel;
     uint32_t num_lights;
     float lights[kMaxLights][4]; // position xyz, intensity (light.h:4-8)
 };

@@ -145,8 +145,21 @@ __device__ __forceinline__ bool sphere_candidate(float cx, float cy, float cz, f
 template <uint32_t KIND>
 __device__ __forceinline__ bool prim_bvh_query(const float4 *__restrict__ nodes, const uint32_t *__restrict__ ids,
                                                const float *__restrict__ lanes, const float o[3], const float d[3], bool any,
-                                               float clip, Hit &hit)
+                                               float clip, Hit &hit, unsigned long long *stats = nullptr)
 {
+    // instrumentation (off unless dodrt_scene_debug_stats enabled it): nodes fetched / primitives tested by this ray
+    struct Count {
+        unsigned long long *stats;
+        uint32_t nodes = 1, prims = 0;
+        __device__ ~Count()
+        {
+            if (stats) {
+                atomicAdd(stats + (KIND == DODRT_KIND_SPHERE ? 0 : 2), (unsigned long long)nodes);
+                atomicAdd(stats + (KIND == DODRT_KIND_SPHERE ? 1 : 3), (unsigned long long)prims);
+                atomicAdd(stats + 4, 1ull);
+            }
+        }
+    } count{stats};
     const float inv[3] = {1.0f / d[0], 1.0f / d[1], 1.0f / d[2]};
     // Near child first: both children of an interior node are tested when it is visited, the one the ray enters first is
     // descended, the other is stacked with its pruning key and dropped unread if a closer candidate turned up meanwhile.
@@ -163,6 +176,7 @@ __device__ __forceinline__ bool prim_bvh_query(const float4 *__restrict__ nodes,
             const uint32_t a = __float_as_uint(lo4.w), b = __float_as_uint(hi4.w);
             if (b & kPrimBvhLeaf) {
                 const uint32_t n = b & ~kPrimBvhLeaf;
+                count.prims += n;
                 for (uint32_t k = 0; k < n; k++) {
                     const uint32_t id = __ldg(ids + a + k);
                     const float *lane = lanes + (size_t)(id >> 3) * (KIND == DODRT_KIND_SPHERE ? 32 : 48);
@@ -193,6 +207,7 @@ __device__ __forceinline__ bool prim_bvh_query(const float4 *__restrict__ nodes,
             } else {
                 const float4 llo = __ldg(nodes + 2 * a), lhi = __ldg(nodes + 2 * a + 1);
                 const float4 rlo = __ldg(nodes + 2 * b), rhi = __ldg(nodes + 2 * b + 1);
+                count.nodes += 2;
                 float keyL = 0.0f, keyR = 0.0f;
                 const bool touchL = prim_bvh_may_touch_key(llo, lhi, o, d, inv, best, keyL);
                 const bool touchR = prim_bvh_may_touch_key(rlo, rhi, o, d, inv, best, keyR);

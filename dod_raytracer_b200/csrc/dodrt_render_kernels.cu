@@ -2,6 +2,10 @@
 // (rayTrace, main.cpp:273-347; getLightingFactor / shadeDiffuse / shadeSpecular / toOutputChannelType,
 // main.cpp:156-244) as a wavefront around the ray-query kernels:
 //
+// The image is walked in the frame's tile / 8x4-block order (slot_to_pixel), so 32 consecutive rays of the first bounce are
+// one coherent pixel block, and a call renders only ITS tiles (first_tile / tile_stride): the reference's split of the
+// frame over its threads (main.cpp:371-394) becomes a split over GPUs (dodrt_multi_render).
+//
 //   render_init      per pixel: primary ray (main.cpp:304-310), finalColor = 0, pixel alive
 //   for k in 0..depth-1:
 //       trace        closest-hit chain for every live pixel's current ray     (launch_trace kModeRays)
@@ -114,16 +118,20 @@ __device__ __forceinline__ void rebuild_record(const DeviceScene &s, const float
 
 __global__ void render_init_kernel(const RenderParams p)
 {
-    const uint64_t pix = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (pix >= (uint64_t)p.width * p.height) {
+    const uint64_t pix = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; // slot of the call's share
+    if (pix >= p.slots) {
         return;
     }
-    const uint32_t col = (uint32_t)(pix % p.width), row = (uint32_t)(pix / p.width);
-    float d[3];
-    primary_dir(__ldg(p.xs + col), __ldg(p.ys + row), d);
+    uint32_t col, row;
+    uint64_t slot;
+    const bool inside = slot_to_pixel(p.frame, p.tiles_x, nullptr, pix, col, row, slot);
+    float d[3] = {0.0f, 0.0f, 1.0f};
+    if (inside) {
+        primary_dir(__ldg(p.xs + col), __ldg(p.ys + row), d);
+    }
     float4 *ray = reinterpret_cast<float4 *>(p.rays + pix);
-    ray[0] = make_float4(p.origin[0], p.origin[1], p.origin[2], d[0]);
-    ray[1] = make_float4(d[1], d[2], kInf, __uint_as_float(0u));
+    ray[0] = make_float4(p.frame.origin[0], p.frame.origin[1], p.frame.origin[2], d[0]);
+    ray[1] = make_float4(d[1], d[2], kInf, __uint_as_float(inside ? 0u : DODRT_RAY_SKIP));
     p.accum[pix] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
 }
 
@@ -131,7 +139,7 @@ __global__ void render_init_kernel(const RenderParams p)
 __global__ void render_shade_kernel(const RenderParams p, uint32_t bounce)
 {
     const uint64_t pix = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (pix >= (uint64_t)p.width * p.height) {
+    if (pix >= p.slots) {
         return;
     }
     float4 *ray = reinterpret_cast<float4 *>(p.rays + pix);
@@ -150,11 +158,13 @@ __global__ void render_shade_kernel(const RenderParams p, uint32_t bounce)
     rebuild_record(p.scene, o, d, h.x, prim, h.z, h.w, P, N, C);
 
     // getLightingFactor, main.cpp:221-244; rayDir is the un-normalised RASTER direction of the pixel (main.cpp:328)
-    const uint32_t col = (uint32_t)(pix % p.width), row = (uint32_t)(pix / p.width);
+    uint32_t col, row;
+    uint64_t slot;
+    slot_to_pixel(p.frame, p.tiles_x, nullptr, pix, col, row, slot); // a live ray belongs to a pixel inside the frame
     const float raster[3] = {__ldg(p.xs + col), __ldg(p.ys + row), 1.0f};
     float lighting = 0.2f; // shadeAmbientFactor
     for (uint32_t l = 0; l < p.num_lights; l++) {
-        if (!p.visible[(uint64_t)l * p.width * p.height + pix]) {
+        if (!p.visible[(uint64_t)l * p.slots + pix]) {
             continue;
         }
         const float L[3] = {p.lights[l][0] - P[0], p.lights[l][1] - P[1], p.lights[l][2] - P[2]};
@@ -191,9 +201,16 @@ __global__ void render_shade_kernel(const RenderParams p, uint32_t bounce)
 __global__ void render_finish_kernel(const RenderParams p)
 {
     const uint64_t pix = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (pix >= (uint64_t)p.width * p.height) {
+    if (pix >= p.slots) {
         return;
     }
+    uint32_t col, row;
+    uint64_t slot;
+    const bool inside = slot_to_pixel(p.frame, p.tiles_x, nullptr, pix, col, row, slot);
+    if (!inside && p.rgb_by_pixel) {
+        return; // a padded slot of an edge tile has no pixel
+    }
+    const uint64_t out = p.rgb_by_pixel ? (uint64_t)row * p.frame.width + col : pix;
     const float4 acc = p.accum[pix];
     const float c[3] = {acc.x, acc.y, acc.z};
 #pragma unroll
@@ -201,7 +218,7 @@ __global__ void render_finish_kernel(const RenderParams p)
         float x = c[k] * 255.0f;
         x = (x < 0.0f) ? 0.0f : x;
         x = (255.0f < x) ? 255.0f : x;
-        p.rgb[pix * 3 + k] = (uint8_t)x;
+        p.rgb[out * 3 + k] = (uint8_t)x;
     }
 }
 
@@ -209,21 +226,21 @@ __global__ void render_finish_kernel(const RenderParams p)
 
 cudaError_t launch_render_init(const RenderParams &p, cudaStream_t stream)
 {
-    const uint64_t n = (uint64_t)p.width * p.height;
+    const uint64_t n = p.slots;
     render_init_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(p);
     return cudaGetLastError();
 }
 
 cudaError_t launch_render_shade(const RenderParams &p, uint32_t bounce, cudaStream_t stream)
 {
-    const uint64_t n = (uint64_t)p.width * p.height;
+    const uint64_t n = p.slots;
     render_shade_kernel<<<(unsigned)((n + 127) / 128), 128, 0, stream>>>(p, bounce);
     return cudaGetLastError();
 }
 
 cudaError_t launch_render_finish(const RenderParams &p, cudaStream_t stream)
 {
-    const uint64_t n = (uint64_t)p.width * p.height;
+    const uint64_t n = p.slots;
     render_finish_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(p);
     return cudaGetLastError();
 }

@@ -44,6 +44,8 @@ class Workload:
     # (nodes, lanes) per ray of the reference traversal: primary over all pixels, shadow over shadow rays
     primary_nodes_lanes: Optional[Tuple[float, float]] = None
     shadow_nodes_lanes: Optional[Tuple[float, float]] = None
+    # config 4 (no kd-tree): bytes per ray of the accelerated sphere / box path incl. io (tests/tools/analytic_bytes.py)
+    explicit_bytes: Optional[Tuple[float, float]] = None
     extra: dict = field(default_factory=dict)
 
     @property
@@ -52,6 +54,8 @@ class Workload:
 
     def algorithmic_bytes(self, shadow_rays: int) -> Tuple[float, float]:
         """(primary kernel bytes, shadow kernel bytes) per launch over the whole frame."""
+        if self.explicit_bytes:
+            return self.pixels * self.explicit_bytes[0], shadow_rays * self.explicit_bytes[1]
         pn, pl = self.primary_nodes_lanes or (0.0, 0.0)
         sn, sl = self.shadow_nodes_lanes or (0.0, 0.0)
         primary = self.pixels * (8.0 * pn + 288.0 * pl + 16.0)  # + 16 B hit record out
@@ -92,6 +96,8 @@ def _load_algorithmic_bytes():
         if w is None:
             continue
         w.primary_nodes_lanes = (e["primary_nodes_per_ray"], e["primary_lanes_per_ray"])
+        if "accelerated_primary" in e:
+            w.explicit_bytes = (e["accelerated_primary"]["bytes"], e["accelerated_shadow"]["bytes"])
         if "shadow_nodes_per_ray" in e:
             w.shadow_nodes_lanes = (e["shadow_nodes_per_ray"], e["shadow_lanes_per_ray"])
         w.extra["counted"] = {k: e[k] for k in ("primary_hits", "shadow_rays", "shadow_visible", "triangles", "kd_nodes",

@@ -197,7 +197,10 @@ DODRT_API int dodrt_trace_frame(dodrt_scene *scene, const dodrt_frame *frame, co
  * reference's shading (main.cpp:156-244), blended with weight 1/2^k; rgb is width*height*3 bytes, row-major
  * (what the reference hands to stbi_write_png, main.cpp:396).  lights: num_lights x {x, y, z, intensity}
  * (light.h:4-8; the reference's nine are main.cpp:283-292), num_lights <= 16.  frame->classes selects the shape
- * classes; tiles/compact are ignored (one GPU renders the whole frame). */
+ * classes.  The call renders ITS tiles (first_tile / tile_stride, like the reference's threads render their row bands,
+ * main.cpp:371-394): with compact = 0 rgb is the whole frame (pixels of other calls' tiles black), with compact = 1 it
+ * holds slots x 3 bytes in the call's own order (dodrt_frame_pixel_map).  dodrt_multi_render renders one frame with all
+ * GPUs of a dodrt_multi into ONE row-major rgb buffer. */
 DODRT_API int dodrt_render(dodrt_scene *scene, const dodrt_frame *frame, const float *xs, const float *ys,
                            const float *lights, uint32_t num_lights, uint32_t depth, uint8_t *rgb);
 
@@ -261,6 +264,8 @@ typedef struct dodrt_multi dodrt_multi; /* opaque */
 DODRT_API int dodrt_multi_create(dodrt_scene *const *scenes, uint32_t num_scenes, dodrt_multi **multi);
 DODRT_API int dodrt_multi_trace_frame(dodrt_multi *multi, const dodrt_frame *frame, const float *xs, const float *ys,
                                       const float *lights, uint32_t num_lights, dodrt_hit *hits, uint8_t *visible);
+DODRT_API int dodrt_multi_render(dodrt_multi *multi, const dodrt_frame *frame, const float *xs, const float *ys,
+                                 const float *lights, uint32_t num_lights, uint32_t depth, uint8_t *rgb);
 DODRT_API int dodrt_multi_destroy(dodrt_multi *multi);
 
 /* Multi-GPU frame assembly (kept for callers that gather compact blocks themselves, e.g. with NCCL; the frame buffer
@@ -279,6 +284,11 @@ DODRT_API int dodrt_frame_local_pixels(const dodrt_frame *frame, uint64_t *slots
 DODRT_API int dodrt_frame_pixel_map(const dodrt_frame *frame, uint32_t *pixel_of_slot, uint64_t slots);
 
 /* ---- instrumentation ------------------------------------------------------------------------- */
+/* Counters of the sphere / box culling structure (measurement only; queries run a little slower while enabled):
+ * reads the counters accumulated since the last call into out (may be NULL) -- [0]/[1] nodes fetched / spheres tested,
+ * [2]/[3] nodes fetched / boxes tested, [4] rays that took a culling structure -- then clears them and switches the
+ * counting on (enable != 0) or off.  Synchronises the device. */
+DODRT_API int dodrt_scene_debug_stats(dodrt_scene *scene, int enable, uint64_t out[8]);
 /* kernels launched by this library on behalf of this scene since creation */
 DODRT_API int dodrt_scene_launch_count(dodrt_scene *scene, uint64_t *launches);
 

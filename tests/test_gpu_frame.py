@@ -229,3 +229,54 @@ def test_scene_on_another_device_than_the_current_one():
         rays["o"][:, 2] = -4.9
         rays["clip"] = np.inf
         assert g1.intersect(rays, ALL).tobytes() == g0.intersect(rays, ALL).tobytes()
+
+
+def _render_host_scene():
+    hs = host.HostScene()
+    hs.add_reference_scene(1, 16)
+    hs.add_mesh_file(f"{GOLDEN}/teapot.dodm")
+    hs.build_tree()
+    return hs
+
+
+def test_render_tile_split_and_multi_gpu():
+    """rayTrace on the GPU (dodrt_render) renders only the call's tiles; the tiles of all ranks together -- compact or
+    full-frame, one GPU after the other or all GPUs of the process at once (dodrt_multi_render, one rgb frame filled in
+    place) -- are the pixels of the one-GPU render, which test_gpu_parity.py pins to the unmodified reference."""
+    import torch
+    from dod_raytracer_b200 import workloads
+    w, h, depth = 250, 141, 4
+    xs, ys = host.ray_tables(w, h)
+    hs = _render_host_scene()
+    with hs.upload(0, shading=True) as g:
+        want = g.render(capi.Frame.make(w, h, classes=ALL), xs, ys, workloads.REFERENCE_LIGHTS, depth)
+        assert want.mean() > 10
+        for world, tile in ((3, (32, 32)), (4, (16, 8))):
+            full = np.zeros((h * w, 3), np.uint8)
+            comp = np.zeros((h * w, 3), np.uint8)
+            for rank in range(world):
+                f0 = capi.Frame.make(w, h, classes=ALL, tile=tile, first_tile=rank, tile_stride=world, compact=0)
+                part = g.render(f0, xs, ys, workloads.REFERENCE_LIGHTS, depth).reshape(-1, 3)
+                f1 = capi.Frame.make(w, h, classes=ALL, tile=tile, first_tile=rank, tile_stride=world, compact=1)
+                m = capi.frame_pixel_map(f1)
+                ok = m != 0xFFFFFFFF
+                mine = np.zeros(h * w, bool)
+                mine[m[ok]] = True
+                assert not part[~mine].any()  # other ranks' pixels stay black
+                full[mine] = part[mine]
+                c = g.render(f1, xs, ys, workloads.REFERENCE_LIGHTS, depth)
+                assert c.shape == (len(m), 3) and not c[~ok].any()
+                comp[m[ok]] = c[ok]
+            assert full.tobytes() == want.tobytes() and comp.tobytes() == want.tobytes(), (world, tile)
+    for n in sorted({1, capi.device_count()}):
+        scenes = [hs.upload(d, shading=True) for d in range(n)]
+        try:
+            with capi.Multi(scenes) as m:
+                got = m.render(capi.Frame.make(w, h, classes=ALL), xs, ys, workloads.REFERENCE_LIGHTS, depth)  # pageable
+                assert got.tobytes() == want.tobytes(), f"{n} GPUs pageable"
+                pinned = torch.zeros((h, w, 3), dtype=torch.uint8).pin_memory().numpy()
+                m.render(capi.Frame.make(w, h, classes=ALL), xs, ys, workloads.REFERENCE_LIGHTS, depth, pinned)
+                assert pinned.tobytes() == want.tobytes(), f"{n} GPUs pinned"
+        finally:
+            for s in scenes:
+                s.close()
