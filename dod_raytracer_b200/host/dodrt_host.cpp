@@ -18,12 +18,55 @@
 #include <limits>
 #include <new>
 #include <string>
+#include <mutex>
+#include <exception>
 #include <thread>
 #include <type_traits>
 #include <unordered_map>
 #include <vector>
 
 namespace {
+
+// Worker threads whose exceptions do not end the process: the first one is kept and re-thrown by join() on the calling
+// thread (from where the C ABI's catch turns it into a status code), and the destructor joins whatever still runs, so
+// an exception on the calling thread never meets a joinable std::thread.
+class ThreadGroup {
+public:
+    template <typename F> void run(F body)
+    {
+        threads_.emplace_back([this, body]() mutable {
+            try {
+                body();
+            } catch (...) {
+                std::lock_guard<std::mutex> lock(mutex_);
+                if (!error_) error_ = std::current_exception();
+            }
+        });
+    }
+    void join()
+    {
+        joinAll();
+        if (error_) {
+            std::exception_ptr e = error_;
+            error_ = nullptr;
+            std::rethrow_exception(e);
+        }
+    }
+    ~ThreadGroup() { joinAll(); }
+
+private:
+    void joinAll()
+    {
+        for (std::thread &t : threads_) {
+            if (t.joinable()) t.join();
+        }
+        threads_.clear();
+    }
+    std::vector<std::thread> threads_;
+    std::mutex mutex_;
+    std::exception_ptr error_;
+};
+
 
 thread_local std::string g_error;
 
@@ -383,10 +426,12 @@ void parseObj(const std::vector<char> &buf, std::vector<Vec3> &pos, std::vector<
         cut[k] = eol ? eol + 1 : end;
     }
     std::vector<ObjChunk> chunks(numChunks);
-    std::vector<std::thread> pool;
-    for (size_t k = 1; k < numChunks; k++) pool.emplace_back([&, k] { parseObjChunk(cut[k], cut[k + 1], chunks[k]); });
-    parseObjChunk(cut[0], cut[1], chunks[0]);
-    for (std::thread &t : pool) t.join();
+    {
+        ThreadGroup pool; // joins on every path; a worker's exception is re-thrown here, on the caller's thread
+        for (size_t k = 1; k < numChunks; k++) pool.run([&, k] { parseObjChunk(cut[k], cut[k + 1], chunks[k]); });
+        parseObjChunk(cut[0], cut[1], chunks[0]);
+        pool.join();
+    }
     size_t seenBefore = 0;
     for (const ObjChunk &c : chunks) {
         for (size_t i = 0; i < c.corners.size(); i++) {
@@ -601,12 +646,19 @@ class TreeBuilder {
         if (fork) {
             // left subtree on another thread, right subtree here, both into private buffers; splice in DFS order
             SubTree leftSub, rightSub;
-            std::thread worker([&] {
-                build(leftSub, depth - 1, badRefines, leftBounds, leftLanes);
-                workers_.fetch_sub(1, std::memory_order_acq_rel);
-            });
-            build(rightSub, depth - 1, badRefines, rightBounds, rightLanes);
-            worker.join();
+            {
+                ThreadGroup worker; // joins on every path; the worker's exception (bad_alloc) is re-thrown by join()
+                struct Release {
+                    std::atomic<unsigned> &n;
+                    ~Release() { n.fetch_sub(1, std::memory_order_acq_rel); }
+                };
+                worker.run([&] {
+                    Release release{workers_};
+                    build(leftSub, depth - 1, badRefines, leftBounds, leftLanes);
+                });
+                build(rightSub, depth - 1, badRefines, rightBounds, rightLanes);
+                worker.join();
+            }
             splice(out, leftSub);
             const uint32_t w0 = splitAxis | ((uint32_t)out.nodes.size() << 2);
             out.nodes[nodeIdx] = (uint64_t)w0 | ((uint64_t)w1 << 32);
@@ -634,7 +686,7 @@ void gatherLanes(const std::vector<T> &in, const std::vector<uint32_t> &primNums
     out.resize(primNums.size());
     const size_t n = primNums.size();
     threads = (unsigned)std::max<size_t>(1, std::min<size_t>(threads, n / 65536 + 1));
-    std::vector<std::thread> pool;
+    ThreadGroup pool;
     for (unsigned t = 0; t < threads; t++) {
         const size_t lo = n * t / threads, hi = n * (t + 1) / threads;
         auto work = [&in, &primNums, &out, lo, hi] {
@@ -643,10 +695,10 @@ void gatherLanes(const std::vector<T> &in, const std::vector<uint32_t> &primNums
         if (t + 1 == threads) {
             work();
         } else {
-            pool.emplace_back(work);
+            pool.run(work);
         }
     }
-    for (std::thread &th : pool) th.join();
+    pool.join();
 }
 
 unsigned hostThreads()
@@ -669,6 +721,24 @@ void appendLane(std::vector<float> &lanes, uint32_t index, uint32_t floatsPerLan
 
 } // namespace
 
+// The ABI never throws: every int-returning entry point is a function-try-block ending in DODRT_HOST_CATCH
+// (std::bad_alloc from the vectors, std::system_error from std::thread in the task-parallel builder, ...).
+static int failException()
+{
+    try {
+        throw;
+    } catch (const std::bad_alloc &) {
+        fail("out of host memory");
+        return DODRT_E_NOMEM;
+    } catch (const std::exception &e) {
+        return fail("unexpected C++ exception: %s", e.what());
+    } catch (...) {
+        return fail("unexpected C++ exception");
+    }
+}
+#define DODRT_HOST_CATCH                                                                                       \
+    catch (...) { return failException(); }
+
 extern "C" {
 
 const char *dodrt_host_last_error(void) { return g_error.c_str(); }
@@ -686,7 +756,7 @@ void dodrt_host_config_defaults(dodrt_host_config *cfg)
 }
 
 int dodrt_host_config_load(const char *path, dodrt_host_config *cfg)
-{
+try {
     if (!path || !cfg) return fail("NULL argument");
     dodrt_host_config_defaults(cfg);
     std::ifstream in(path);
@@ -716,9 +786,10 @@ int dodrt_host_config_load(const char *path, dodrt_host_config *cfg)
     }
     return DODRT_OK;
 }
+DODRT_HOST_CATCH
 
 int dodrt_host_scene_create(const dodrt_host_config *cfg, dodrt_host_scene **scene)
-{
+try {
     if (!scene) return fail("scene is NULL");
     dodrt_host_scene *s = new (std::nothrow) dodrt_host_scene();
     if (!s) return DODRT_E_NOMEM;
@@ -727,20 +798,22 @@ int dodrt_host_scene_create(const dodrt_host_config *cfg, dodrt_host_scene **sce
     *scene = s;
     return DODRT_OK;
 }
+DODRT_HOST_CATCH
 
 void dodrt_host_scene_destroy(dodrt_host_scene *scene) { delete scene; }
 
 int dodrt_host_add_mesh(dodrt_host_scene *s, const float *positions, uint32_t numVertices, const uint32_t *indices,
                         uint32_t numTriangles, const float transform[4])
-{
+try {
     if (!s || (!positions && numVertices) || (!indices && numTriangles)) return fail("NULL argument");
     std::vector<Vec3> pos(numVertices);
     for (uint32_t i = 0; i < numVertices; i++) pos[i] = Vec3{positions[i * 3], positions[i * 3 + 1], positions[i * 3 + 2]};
     return addMesh(s, pos, indices, numTriangles, transform);
 }
+DODRT_HOST_CATCH
 
 int dodrt_host_add_mesh_file(dodrt_host_scene *s, const char *path, const float transform[4])
-{
+try {
     if (!s || !path) return fail("NULL argument");
     std::vector<char> buf;
     if (!readFile(path, buf)) return fail("cannot read %s", path); // mesh.cpp:17-21 prints and returns
@@ -761,9 +834,10 @@ int dodrt_host_add_mesh_file(dodrt_host_scene *s, const char *path, const float 
     if (idx.empty()) return fail("%s: no faces", path);
     return addMesh(s, pos, idx.data(), (uint32_t)(idx.size() / 3), transform);
 }
+DODRT_HOST_CATCH
 
 int dodrt_host_standin_dragon(uint32_t n, float *positions, uint32_t *indices)
-{
+try {
     if (n < 3 || !positions || !indices) return fail("bad argument");
     const double pi = 3.14159265358979323846;
     const uint32_t stride = n + 1;
@@ -788,10 +862,11 @@ int dodrt_host_standin_dragon(uint32_t n, float *positions, uint32_t *indices)
     }
     return DODRT_OK;
 }
+DODRT_HOST_CATCH
 
 int dodrt_host_write_dodm(const char *path, const float *positions, uint32_t numVertices, const uint32_t *indices,
                           uint32_t numTriangles)
-{
+try {
     FILE *f = std::fopen(path, "wb");
     if (!f) return fail("cannot write %s", path);
     const uint32_t hdr[2] = {numVertices, numTriangles};
@@ -801,9 +876,10 @@ int dodrt_host_write_dodm(const char *path, const float *positions, uint32_t num
     std::fclose(f);
     return ok ? DODRT_OK : fail("short write to %s", path);
 }
+DODRT_HOST_CATCH
 
 int dodrt_host_add_sphere(dodrt_host_scene *s, const float pos[3], float radius, const float color[3])
-{
+try {
     if (!s || !pos) return fail("NULL argument");
     const float vals[4] = {pos[0], pos[1], pos[2], radius * radius}; // sphere.cpp:234-238
     appendLane(s->sphereLanes, s->numSpheres, 4 * kLane, vals, 4);
@@ -811,9 +887,10 @@ int dodrt_host_add_sphere(dodrt_host_scene *s, const float pos[3], float radius,
     s->numSpheres++;
     return DODRT_OK;
 }
+DODRT_HOST_CATCH
 
 int dodrt_host_add_plane(dodrt_host_scene *s, const float normal[3], const float pos[3], const float color[3])
-{
+try {
     if (!s || !normal || !pos) return fail("NULL argument");
     const float vals[6] = {pos[0], pos[1], pos[2], normal[0], normal[1], normal[2]}; // plane.cpp:212-217
     appendLane(s->planeLanes, s->numPlanes, 6 * kLane, vals, 6);
@@ -821,9 +898,10 @@ int dodrt_host_add_plane(dodrt_host_scene *s, const float normal[3], const float
     s->numPlanes++;
     return DODRT_OK;
 }
+DODRT_HOST_CATCH
 
 int dodrt_host_add_cylinder(dodrt_host_scene *s, float radius, float height, const float axis[3], const float base[3])
-{
+try {
     if (!s || !axis || !base) return fail("NULL argument");
     dodrt_cylinder c; // Cylinder::Cylinder, cylinder.cpp:223-229: axis = glm::normalize(axis) = v * (1/sqrt(dot))
     const Vec3 a{axis[0], axis[1], axis[2]};
@@ -837,18 +915,20 @@ int dodrt_host_add_cylinder(dodrt_host_scene *s, float radius, float height, con
     s->cylinders.push_back(c);
     return DODRT_OK;
 }
+DODRT_HOST_CATCH
 
 int dodrt_host_add_box(dodrt_host_scene *s, const float lo[3], const float hi[3])
-{
+try {
     if (!s || !lo || !hi) return fail("NULL argument");
     const float vals[6] = {lo[0], lo[1], lo[2], hi[0], hi[1], hi[2]};
     appendLane(s->boxLanes, s->numBoxes, 6 * kLane, vals, 6);
     s->numBoxes++;
     return DODRT_OK;
 }
+DODRT_HOST_CATCH
 
 int dodrt_host_add_reference_scene(dodrt_host_scene *s, uint32_t seed, uint32_t numSpheres)
-{
+try {
     if (!s) return fail("NULL argument");
     GlibcRand rnd(seed); // srand(seed) in place of srand(time(NULL)), main.cpp:351
     for (uint32_t i = 0; i < numSpheres; i++) { // generateSpheres, main.cpp:26-50: r g b x y z
@@ -872,9 +952,10 @@ int dodrt_host_add_reference_scene(dodrt_host_scene *s, uint32_t seed, uint32_t 
     for (int k = 0; k < 3; k++) (void)rnd();
     return dodrt_host_add_cylinder(s, 1.5f, 4.0f, axis, base);
 }
+DODRT_HOST_CATCH
 
 int dodrt_host_add_analytic_scene(dodrt_host_scene *s, uint32_t seed, uint32_t count)
-{
+try {
     if (!s) return fail("NULL argument");
     uint32_t x = seed;
     auto draw = [&x]() {
@@ -894,9 +975,10 @@ int dodrt_host_add_analytic_scene(dodrt_host_scene *s, uint32_t seed, uint32_t c
     }
     return DODRT_OK;
 }
+DODRT_HOST_CATCH
 
 int dodrt_host_build_tree_ex(dodrt_host_scene *s, uint32_t flags)
-{
+try {
     if (!s) return fail("NULL argument");
     if (s->built) return fail("tree already built");
     if (flags & ~(uint32_t)DODRT_HOST_BUILD_KEEP_CREATION_ORDER) return fail("unknown build flags 0x%x", flags);
@@ -934,11 +1016,12 @@ int dodrt_host_build_tree_ex(dodrt_host_scene *s, uint32_t flags)
     s->built = true;
     return DODRT_OK;
 }
+DODRT_HOST_CATCH
 
 int dodrt_host_build_tree(dodrt_host_scene *s) { return dodrt_host_build_tree_ex(s, 0); }
 
 int dodrt_host_sizes_get(const dodrt_host_scene *s, dodrt_host_sizes *z)
-{
+try {
     if (!s || !z) return fail("NULL argument");
     z->num_triangles = s->numTriangles;
     z->num_orig_lanes = s->built ? s->numOrigLanes : (uint32_t)s->lanes.size();
@@ -951,6 +1034,7 @@ int dodrt_host_sizes_get(const dodrt_host_scene *s, dodrt_host_sizes *z)
     z->num_boxes = s->numBoxes;
     return DODRT_OK;
 }
+DODRT_HOST_CATCH
 
 const uint64_t *dodrt_host_nodes(const dodrt_host_scene *s) { return s->nodes.data(); }
 const float *dodrt_host_tri_lanes(const dodrt_host_scene *s) { return reinterpret_cast<const float *>(s->lanes.data()); }
@@ -969,7 +1053,7 @@ const float *dodrt_host_box_lanes(const dodrt_host_scene *s) { return s->boxLane
 float dodrt_host_epsilon(const dodrt_host_scene *s) { return s->cfg.epsilon; }
 
 int dodrt_host_ray_tables(uint32_t width, uint32_t height, float *xs, float *ys)
-{
+try {
     if (!width || !height || !xs || !ys) return fail("bad argument");
     const float ratio = (float)width / height; // Config::Ratio, config.h:27
     const float widthStep = 2.0f * ratio / width; // main.cpp:278-279
@@ -986,5 +1070,6 @@ int dodrt_host_ray_tables(uint32_t width, uint32_t height, float *xs, float *ys)
     }
     return DODRT_OK;
 }
+DODRT_HOST_CATCH
 
 } // extern "C"
