@@ -1,4 +1,5 @@
-"""SASS audit of the packed-fp32 first stage (variant 6, csrc/dodrt_device.cuh "packed fp32 pairs").
+"""SASS audit of the packed-fp32 first stage (variant 6, csrc/dodrt_device.cuh "packed fp32 pairs"; an A/B experiment that
+lives in lib/libdodrt_cuda_exp.so since round 2 -- the product library must not contain packed fp32 arithmetic at all).
 
 ptxas 12.9 contracts mul.rn.f32x2 + add.rn.f32x2 into FFMA2 even under --fmad=false, which would change the bits of
 det / dot(T, pvec) relative to the reference's un-fused AVX arithmetic (triangle.cpp:66-93).  The kernels therefore
@@ -17,9 +18,11 @@ from dod_raytracer_b200 import capi
 
 @pytest.mark.skipif(shutil.which("cuobjdump") is None, reason="cuobjdump not on PATH")
 def test_packed_multiplies_are_not_contracted():
-    if not os.path.exists(capi.LIB_PATH):
-        pytest.skip("library not built")
-    sass = subprocess.run(["cuobjdump", "-sass", capi.LIB_PATH], check=True, capture_output=True, text=True).stdout
+    if not os.path.exists(capi.EXP_LIB_PATH) or not os.path.exists(capi.LIB_PATH):
+        pytest.skip("libraries not built")
+    product = subprocess.run(["cuobjdump", "-sass", capi.LIB_PATH], check=True, capture_output=True, text=True).stdout
+    assert not re.search(r"\b(FFMA2|FMUL2|FADD2)\b", product), "packed fp32 arithmetic in the product library"
+    sass = subprocess.run(["cuobjdump", "-sass", capi.EXP_LIB_PATH], check=True, capture_output=True, text=True).stdout
     ffma2 = [l for l in sass.splitlines() if re.search(r"\bFFMA2\b", l)]
     fadd2 = [l for l in sass.splitlines() if re.search(r"\bFADD2\b", l)]
     fmul2 = [l for l in sass.splitlines() if re.search(r"\bFMUL2\b", l)]
