@@ -116,6 +116,13 @@ struct dodrt_scene {
     std::mutex mutex; // guards scene mutation and the lazily created staging stream
     cudaStream_t stream = nullptr;
     cudaStream_t copyStream = nullptr; // D2H of finished bands while the next band is traced
+    // Frame shares traced in CHUNKS on concurrent streams (traceFrameOnDevice): chunk c's primary / shadow passes run on
+    // chunkStream[c-1] (chunk 0 on the caller's stream), fenced with events from a recycled ring
+    static constexpr int kMaxChunks = 4;
+    cudaStream_t chunkStream[kMaxChunks - 1] = {nullptr, nullptr, nullptr};
+    static constexpr int kChunkEvents = 64;
+    cudaEvent_t chunkEvent[kChunkEvents] = {};
+    std::atomic<uint32_t> nextChunkEvent{0};
     // staging memory of the host-buffer entry points: a private pool that keeps freed blocks cached
     // (release threshold = max), so a per-frame call does not pay for physical allocation every time
     cudaMemPool_t pool = nullptr;
@@ -491,6 +498,41 @@ int launchFrameFused(dodrt_scene *s, const dodrt_frame *frame, const float *d_xs
 }
 
 // The whole frame share: fused launch when the variant has one, else primary pass + one shadow pass per light.
+int ensureChunkStreams(dodrt_scene *s)
+{
+    std::lock_guard<std::mutex> lock(s->mutex);
+    if (s->chunkEvent[0]) return DODRT_OK;
+    DeviceGuard guard(s->device);
+    if (!guard.ok) return fail(DODRT_E_CUDA, "cannot select device %d", s->device);
+    for (cudaStream_t &cs : s->chunkStream) CUDA_TRY(cudaStreamCreateWithFlags(&cs, cudaStreamNonBlocking));
+    for (int i = dodrt_scene::kChunkEvents - 1; i >= 0; i--) { // [0] last: it doubles as the "all created" flag
+        CUDA_TRY(cudaEventCreateWithFlags(&s->chunkEvent[i], cudaEventDisableTiming));
+    }
+    return DODRT_OK;
+}
+
+cudaEvent_t nextChunkEvent(dodrt_scene *s) { return s->chunkEvent[s->nextChunkEvent.fetch_add(1) % dodrt_scene::kChunkEvents]; }
+
+// In how many chunks is this frame share traced?  A/B knob (DODRT_FRAME_CHUNKS, default 1).  The idea: a short share (a rank
+// of a split frame) ends each of its passes with a tail in which a few warps finish long rays while most SMs idle (about
+// 160 us per pass on a 1-of-8 share of a 4K frame); cut into halves whose passes run on two streams, the tail of one half's
+// pass could overlap the main phase of the other's next pass -- idle warps leave the persistent kernel (helper limit), their
+// SM slots go to the other stream's kernel, and no kernel ever waits for another one.  MEASURED (tests/tools/chunk_sweep.sh,
+// 1-of-8 share of dragon4k): 1 chunk 0.714 ms, 2 chunks 0.855, 4 chunks 1.063 (N=1: 3.82 -> 4.27): every kernel is a
+// persistent grid sized for the whole GPU, so two of them in flight halve each other's resident warps and mix closest-hit and
+// any-hit programs on an SM, which costs more than the overlapped tails give (same finding as the one-launch frame kernels,
+// profiles/r02_frame_kernel_ab.txt).
+uint32_t frameChunks(const dodrt_frame *frame, uint32_t tiles)
+{
+    const char *e = std::getenv("DODRT_FRAME_CHUNKS"); // read per call (A/B)
+    uint32_t chunks = e ? (uint32_t)std::max(1, std::atoi(e)) : 1u;
+    (void)frame;
+    chunks = std::min<uint32_t>(chunks, dodrt_scene::kMaxChunks);
+    while (chunks > 1 && tiles / chunks < 128) chunks--; // a chunk is still a few batches per warp
+    return chunks;
+}
+
+// The whole frame share: primary pass + one shadow pass per light (experiments build, DODRT_FUSED=1: one launch).
 int traceFrameOnDevice(dodrt_scene *s, const dodrt_frame *frame, const float *d_xs, const float *d_ys, const float *lights,
                        uint32_t numLights, dodrt_hit *d_hits, uint8_t *d_visible, uint64_t visStride, const Mirror *mirror,
                        cudaStream_t stream)
@@ -498,15 +540,34 @@ int traceFrameOnDevice(dodrt_scene *s, const dodrt_frame *frame, const float *d_
     bool done = false;
     int rc = launchFrameFused(s, frame, d_xs, d_ys, lights, numLights, d_hits, d_visible, visStride, mirror, stream, &done);
     if (rc != DODRT_OK || done) return rc;
-    rc = launchFrame(s, kModePrimary, frame, d_xs, d_ys, d_hits, nullptr, nullptr, stream, 0, 0xFFFFFFFFu, mirror);
-    for (uint32_t l = 0; l < numLights && rc == DODRT_OK; l++) {
-        Mirror m;
-        if (mirror) {
-            m = *mirror;
-            m.visible = mirror->visible ? mirror->visible + (uint64_t)l * mirror->lightStride : nullptr;
+    uint32_t tilesX, tiles;
+    frameTiles(frame, &tilesX, &tiles);
+    const uint32_t chunks = frameChunks(frame, tiles);
+    if (chunks > 1) {
+        rc = ensureChunkStreams(s);
+        if (rc != DODRT_OK) return rc;
+        cudaEvent_t fork = nextChunkEvent(s);
+        CUDA_TRY(cudaEventRecord(fork, stream));
+        for (uint32_t c = 1; c < chunks; c++) CUDA_TRY(cudaStreamWaitEvent(s->chunkStream[c - 1], fork, 0));
+    }
+    for (uint32_t c = 0; c < chunks && rc == DODRT_OK; c++) {
+        cudaStream_t st = c == 0 ? stream : s->chunkStream[c - 1];
+        const uint32_t begin = (uint32_t)((uint64_t)tiles * c / chunks), end = (uint32_t)((uint64_t)tiles * (c + 1) / chunks);
+        rc = launchFrame(s, kModePrimary, frame, d_xs, d_ys, d_hits, nullptr, nullptr, st, begin, end - begin, mirror);
+        for (uint32_t l = 0; l < numLights && rc == DODRT_OK; l++) {
+            Mirror m;
+            if (mirror) {
+                m = *mirror;
+                m.visible = mirror->visible ? mirror->visible + (uint64_t)l * mirror->lightStride : nullptr;
+            }
+            rc = launchFrame(s, kModeShadow, frame, d_xs, d_ys, d_hits, lights + 3 * l, d_visible + (uint64_t)l * visStride, st, begin,
+                             end - begin, mirror ? &m : nullptr);
         }
-        rc = launchFrame(s, kModeShadow, frame, d_xs, d_ys, d_hits, lights + 3 * l, d_visible + (uint64_t)l * visStride, stream, 0,
-                         0xFFFFFFFFu, mirror ? &m : nullptr);
+    }
+    for (uint32_t c = 1; c < chunks; c++) { // join: the caller's stream continues when every chunk is done
+        cudaEvent_t joined = nextChunkEvent(s);
+        CUDA_TRY(cudaEventRecord(joined, s->chunkStream[c - 1]));
+        CUDA_TRY(cudaStreamWaitEvent(stream, joined, 0));
     }
     return rc;
 }
@@ -632,6 +693,12 @@ try {
     cudaDeviceSynchronize();
     if (s->stream) cudaStreamDestroy(s->stream);
     if (s->copyStream) cudaStreamDestroy(s->copyStream);
+    for (cudaStream_t cs : s->chunkStream) {
+        if (cs) cudaStreamDestroy(cs);
+    }
+    for (cudaEvent_t ev : s->chunkEvent) {
+        if (ev) cudaEventDestroy(ev);
+    }
     if (s->pool) cudaMemPoolDestroy(s->pool);
     for (cudaEvent_t ev : s->stEvents) cudaEventDestroy(ev);
     if (s->stTables) cudaFree(s->stTables);

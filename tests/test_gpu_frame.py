@@ -130,6 +130,30 @@ def test_fused_tile_split_with_frame_buffer_mirror(teapot):
             _device_frame(g, capi.Frame.make(w, h, classes=ALL), xs, ys, LIGHTS2, mirror=small)
 
 
+@pytest.mark.parametrize("chunks", [2, 4])
+def test_frame_share_in_chunks_on_concurrent_streams(teapot, monkeypatch, chunks):
+    """A rank's share is cut into chunks whose primary / shadow passes run on concurrent streams so that one chunk's tail
+    overlaps the other's main phase.  Same bytes, locally and in the mirror, full frame and share."""
+    g = teapot
+    w, h = 1920, 1080
+    xs, ys = host.ray_tables(w, h)
+    for kw in (dict(), dict(first_tile=1, tile_stride=2, compact=1)):
+        frame = capi.Frame.make(w, h, classes=ALL, **kw)
+        monkeypatch.setenv("DODRT_FRAME_CHUNKS", "1")
+        want_h, want_v = _device_frame(g, frame, xs, ys, LIGHTS2)
+        monkeypatch.setenv("DODRT_FRAME_CHUNKS", str(chunks))
+        with capi.FrameBuffer.create(g, w, h, 2) as fb:
+            got_h, got_v = _device_frame(g, frame, xs, ys, LIGHTS2, mirror=fb)
+            assert got_h.tobytes() == want_h.tobytes() and got_v.tobytes() == want_v.tobytes()
+            fh, fv = _read_frame_buffer(fb, w, h, 2)
+            if frame.compact:
+                m = capi.frame_pixel_map(frame)
+                ok = m != 0xFFFFFFFF
+                assert fh[m[ok]].tobytes() == want_h[ok].tobytes() and fv[:, m[ok]].tobytes() == want_v[:, ok].tobytes()
+            else:
+                assert fh.tobytes() == want_h.tobytes() and fv.tobytes() == want_v.tobytes()
+
+
 def test_host_buffers_zero_copy_equals_staged(teapot, monkeypatch):
     """dodrt_trace_frame with PINNED host buffers lets the kernel store the results into them (no D2H copies);
     pageable buffers are staged.  Same bytes, full-frame and compact (padded slots included)."""
