@@ -479,17 +479,15 @@ def main():
     value = rays_per_step / (ms_per_step * 1e-3) / 1e6
     res_hits, res_vis = assembled_frame() if rank == 0 else (None, None)
 
-    # ---- e2e: host buffers through the C ABI, every rank its own tiles.  The caller's buffers are pinned, so the kernel
-    # delivers every record into them itself (dodrt_trace_frame's zero-copy path); the call returns when they are there.
+    # ---- e2e: host buffers through the C ABI, every rank its own tiles; the call returns when every record is in the
+    # caller's (pinned) host buffers.
     e2e = None
     if not args.no_e2e:
         h_hits = torch.empty((slots, 16), dtype=torch.uint8, pin_memory=True).numpy().reshape(-1).view(capi.HIT_DT)
         h_vis = torch.empty((max(nl, 1), slots), dtype=torch.uint8, pin_memory=True).numpy()
         h_xs = torch.from_numpy(xs).pin_memory().numpy()
         h_ys = torch.from_numpy(ys).pin_memory().numpy()
-        # warm-up: 5 calls -- the library spends the first four per frame shape measuring staged vs zero-copy delivery
-        # (two each, include/dodrt.h) and keeps the faster from the fifth on
-        for _ in range(5):
+        for _ in range(3):
             scene.trace_frame(frame, h_xs, h_ys, lights[:nl], h_hits, h_vis)
         sync_all()
         t_e2e = 0.0
@@ -507,8 +505,7 @@ def main():
         e2e = {"value": rays_per_step / e2e_s / 1e6, "unit": UNIT, "ms_per_step": e2e_s * 1e3,
                "h2d_bytes_per_step": int(xs.nbytes + ys.nbytes) * world,
                "d2h_bytes_per_step": int(w.pixels * (16 + nl)) if world == 1 else int(slots_rank0 * (16 + nl)) * world,
-               "api": "dodrt_trace_frame (pinned host buffers; the library measured staged copies vs direct stores by the kernel for "
-                      "this frame shape during warm-up and uses the faster)",
+               "api": "dodrt_trace_frame (pinned host buffers; persistent staging, hit-record D2H overlapped with the shadow pass)",
                "steps": args.steps, "host_results_equal_device_results": same}
 
     if rank != 0:

@@ -9,7 +9,6 @@
 
 #include <algorithm>
 #include <atomic>
-#include <chrono>
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
@@ -149,17 +148,6 @@ struct dodrt_scene {
     size_t stVisBytes = 0;
     std::vector<cudaEvent_t> stEvents;
     size_t stEventsUsed = 0;
-    // dodrt_trace_frame with pinned host buffers can deliver the results in two ways (identical bytes): staged (device
-    // buffers + DMA copies overlapped with the shadow pass) or zero-copy (the kernel stores them over PCIe itself).
-    // Which one is faster depends on the share: SM stores reach about half the DMA bandwidth, so a whole 4K frame
-    // (141 MB) is faster staged and a 1-of-8 share (18 MB, one short launch) faster zero-copy.  The scene measures:
-    // per frame shape, calls 1-2 run staged, 3-4 zero-copy (the second of each pair is timed), then the faster stays.
-    struct HostPathChoice {
-        uint64_t key = 0;
-        uint32_t calls = 0;
-        double stagedMs = 0, zeroCopyMs = 0;
-    };
-    std::vector<HostPathChoice> hostPaths;
 };
 
 // dodrt_frame_buffer: a row-major frame in one GPU's HBM that kernels on other GPUs write into (include/dodrt.h)
@@ -1367,40 +1355,15 @@ try {
     if (e == cudaSuccess) {
         e = cudaMemcpyAsync(d_tables + frame->width, ys, frame->height * sizeof(float), cudaMemcpyHostToDevice, st);
     }
-    // ---- zero-copy: the caller's buffers are pinned host memory this GPU can address.  The kernels write every result
-    // there themselves, next to the device copy the shadow queue reads (TraceParams::mirror_*): 128-byte rows of hit
-    // records stream over PCIe WHILE the frame is traced, nothing is copied afterwards, and the whole share is one fused
-    // launch.  (Full-frame results of a tile split also need the other ranks' pixels cleared: staged path below.)
-    const char *zcEnv = std::getenv("DODRT_ZEROCOPY"); // read per call: 0 = always stage + copy, 1 = zero-copy whenever possible
-    const int zcMode = zcEnv ? (std::atoi(zcEnv) != 0 ? 1 : 0) : -1; // -1: measure and keep the faster (HostPathChoice)
-    void *mHits = zcMode != 0 ? mappedHostPointer(hits, slots * sizeof(dodrt_hit)) : nullptr;
-    void *mVis = (zcMode != 0 && num_lights) ? mappedHostPointer(visible, slots * (size_t)num_lights) : nullptr;
-    bool zeroCopy = mHits && (num_lights == 0 || mVis) && (frame->compact || frame->tile_stride == 1);
-    dodrt_scene::HostPathChoice *choice = nullptr;
-    if (zeroCopy && zcMode < 0) {
-        const uint64_t key = (slots << 8) ^ ((uint64_t)num_lights << 3) ^ (frame->compact ? 4u : 0u) ^ ((uint64_t)frame->tile_stride << 40);
-        for (auto &c : s->hostPaths) {
-            if (c.key == key) choice = &c;
-        }
-        if (!choice) {
-            s->hostPaths.emplace_back();
-            choice = &s->hostPaths.back();
-            choice->key = key;
-        }
-        const uint32_t call = choice->calls++;
-        if (call >= 4) {
-            zeroCopy = choice->zeroCopyMs < choice->stagedMs;
-            choice = nullptr; // decided: nothing left to measure
-        } else {
-            zeroCopy = call >= 2;
-        }
-    }
-    const auto hostT0 = std::chrono::steady_clock::now();
-    auto noteTime = [&](bool wasZeroCopy) {
-        if (!choice || (choice->calls != 2 && choice->calls != 4)) return; // the second call of each pair counts
-        const double ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - hostT0).count();
-        (wasZeroCopy ? choice->zeroCopyMs : choice->stagedMs) = ms;
-    };
+    // ---- zero-copy.  Opt-in (DODRT_ZEROCOPY=1, read per call): the kernels store every result into the caller's PINNED buffers themselves
+    // (mirror = the host buffers) instead of staging + DMA copies.  Measured on this pool's B200s it loses at every share
+    // size -- SM stores over PCIe reach about half the DMA rate and stall the SMs (dragon4k: 5.85 vs 3.99 ms whole frame,
+    // 0.96 vs 0.77 ms for a 1-of-8 share; tests/tools/e2e_probe.py) -- so the default is the staged path below.
+    const char *zcEnv = std::getenv("DODRT_ZEROCOPY");
+    const bool zcOn = zcEnv && std::atoi(zcEnv) != 0;
+    void *mHits = zcOn ? mappedHostPointer(hits, slots * sizeof(dodrt_hit)) : nullptr;
+    void *mVis = (zcOn && num_lights) ? mappedHostPointer(visible, slots * (size_t)num_lights) : nullptr;
+    const bool zeroCopy = mHits && (num_lights == 0 || mVis) && (frame->compact || frame->tile_stride == 1);
     if (e == cudaSuccess && zeroCopy) {
         Mirror m;
         m.hits = static_cast<dodrt_hit *>(mHits);
@@ -1411,7 +1374,6 @@ try {
         cudaError_t es = cudaStreamSynchronize(st);
         if (rc != DODRT_OK) return rc;
         if (es != cudaSuccess) return fail(DODRT_E_CUDA, "dodrt_trace_frame: %s", cudaGetErrorString(es));
-        noteTime(true);
         return DODRT_OK;
     }
     if (e == cudaSuccess && !frame->compact) {
@@ -1476,7 +1438,6 @@ try {
     if (e == cudaSuccess) e = ec;
     if (e == cudaSuccess) e = es;
     if (e != cudaSuccess) return fail(DODRT_E_CUDA, "dodrt_trace_frame: %s", cudaGetErrorString(e));
-    noteTime(false);
     return DODRT_OK;
 }
 DODRT_CATCH

@@ -155,8 +155,8 @@ def test_frame_share_in_chunks_on_concurrent_streams(teapot, monkeypatch, chunks
 
 
 def test_host_buffers_zero_copy_equals_staged(teapot, monkeypatch):
-    """dodrt_trace_frame with PINNED host buffers lets the kernel store the results into them (no D2H copies);
-    pageable buffers are staged.  Same bytes, full-frame and compact (padded slots included)."""
+    """dodrt_trace_frame with PINNED host buffers and DODRT_ZEROCOPY=1 lets the kernels store the results into them (no D2H
+    copies; opt-in, measured slower than staging on this pool).  Same bytes, full-frame and compact (padded slots included)."""
     import torch
     g = teapot
     w, h = 1000, 562
@@ -177,13 +177,12 @@ def test_host_buffers_zero_copy_equals_staged(teapot, monkeypatch):
         g.trace_frame(frame, xs, ys, LIGHTS2[:0], ph, None)
         assert ph.tobytes() == want_h.tobytes()
         assert g.launch_count() > before
-        # default: the scene measures both ways for this frame shape (2 + 2 calls) and keeps the faster -- same bytes always
+        # default (no knob): staged copies into the pinned buffers
         monkeypatch.delenv("DODRT_ZEROCOPY")
-        for _ in range(6):
-            ph[:] = np.zeros(1, capi.HIT_DT)
-            pv[:] = 7
-            g.trace_frame(frame, xs, ys, LIGHTS2, ph, pv)
-            assert ph.tobytes() == want_h.tobytes() and pv.tobytes() == want_v.tobytes()
+        ph[:] = np.zeros(1, capi.HIT_DT)
+        pv[:] = 7
+        g.trace_frame(frame, xs, ys, LIGHTS2, ph, pv)
+        assert ph.tobytes() == want_h.tobytes() and pv.tobytes() == want_v.tobytes()
 
 
 def test_frame_buffer_shared_with_another_process(tmp_path):
