@@ -15,7 +15,7 @@ import numpy as np
 from . import capi
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libdodrt_host.so")
+LIB_PATH = os.environ.get("DODRT_HOST_LIB") or os.path.join(_HERE, "lib", "libdodrt_host.so")
 BUILD_KEEP_CREATION_ORDER = 1  # DODRT_HOST_BUILD_KEEP_CREATION_ORDER (include/dodrt_host.h)
 
 
