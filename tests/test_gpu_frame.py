@@ -58,11 +58,9 @@ def _read_frame_buffer(fb, w, h, nl, device=0):
     return hits, vis
 
 
-@pytest.fixture(scope="module", params=[-1, 3, 7, 0], ids=lambda v: f"variant{v}")
+@pytest.fixture(scope="module", params=[v for v in (-1, 3, 7, 0) if capi.variant_available(v)], ids=lambda v: f"variant{v}")
 def teapot(request):
     """auto / plain fused / donating fused / a variant without a fused form (falls back to separate passes)"""
-    if not capi.variant_available(request.param):
-        pytest.skip("experiment variant")
     g = upload(teapot_scene(full=True))
     g.set_kernel_variant(request.param)
     g.variant = request.param
