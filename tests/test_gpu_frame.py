@@ -301,3 +301,33 @@ def test_render_tile_split_and_multi_gpu():
         finally:
             for s in scenes:
                 s.close()
+
+
+def test_ragged_and_degenerate_frames(oracle):
+    """Edge cases of the frame description: 1x1 and 7x3 images (smaller than one 8x4 block), tiles larger than the image,
+    the largest tile the ABI accepts, a share with no tile at all, 16 lights, no light -- against the oracle."""
+    scene = teapot_scene(full=True)
+    lights16 = np.stack([np.array([np.cos(k) * 3.0, 2.0 + 0.1 * k, np.sin(k) * 3.0], np.float32) for k in range(16)])
+    with upload(scene) as g:
+        for (w, h, tile) in ((1, 1, (8, 4)), (7, 3, (8, 4)), (33, 17, (64, 64)), (100, 50, (4096, 4096)), (97, 61, (16, 4))):
+            xs, ys = host.ray_tables(w, h)
+            want = oracle.trace_primary(scene, w, h, ALL, nthreads=4)
+            frame = capi.Frame.make(w, h, classes=ALL, tile=tile)
+            hits, vis = g.trace_frame(frame, xs, ys, lights16)
+            assert hits.tobytes() == want.tobytes(), (w, h, tile)
+            for l in (0, 7, 15):
+                assert vis[l].tobytes() == oracle.trace_shadow(scene, w, h, ALL, want, lights16[l], nthreads=4).tobytes(), (w, h, l)
+            h0, v0 = g.trace_frame(frame, xs, ys, lights16[:0])
+            assert h0.tobytes() == want.tobytes() and v0.size == 0
+            # a rank beyond the last tile has nothing to do and says so
+            empty = capi.Frame.make(w, h, classes=ALL, tile=tile, first_tile=10 ** 6, tile_stride=2, compact=1)
+            assert capi.frame_local_pixels(empty) == 0
+            eh, ev = g.trace_frame(empty, xs, ys, lights16[:1])
+            assert len(eh) == 0
+        with pytest.raises(capi.DodrtError):  # tile sides are bounded (checkFrame)
+            g.trace_frame(capi.Frame.make(64, 64, classes=ALL, tile=(8192, 4)), *host.ray_tables(64, 64), lights16[:1])
+        with pytest.raises(capi.DodrtError):  # more lights than the render / frame kernels carry
+            import torch
+            d = torch.zeros(64, dtype=torch.uint8, device="cuda")
+            g.trace_frame_device(capi.Frame.make(8, 4, classes=ALL), d.data_ptr(), d.data_ptr(), np.zeros((17, 3), np.float32),
+                                 d.data_ptr(), d.data_ptr())
