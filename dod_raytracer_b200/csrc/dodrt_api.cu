@@ -1462,13 +1462,15 @@ try {
     cudaStream_t st = s->stream;
     const uint64_t slots = frame->compact ? frameSlots(frame) : (uint64_t)frame->width * frame->height;
     if (slots == 0) return DODRT_OK;
-    float *d_tables = nullptr;
-    dodrt_hit *d_hits = nullptr;
-    uint8_t *d_vis = nullptr;
-    CUDA_TRY(cudaMallocFromPoolAsync(&d_tables, ((size_t)frame->width + frame->height) * sizeof(float), s->pool, st));
-    cudaError_t e = cudaMallocFromPoolAsync(&d_hits, slots * sizeof(dodrt_hit), s->pool, st);
-    if (e == cudaSuccess) e = cudaMallocFromPoolAsync(&d_vis, slots, s->pool, st);
-    if (e == cudaSuccess) e = cudaMemcpyAsync(d_tables, xs, frame->width * sizeof(float), cudaMemcpyHostToDevice, st);
+    std::lock_guard<std::mutex> hostLock(s->hostMutex); // persistent staging, like dodrt_trace_frame
+    cudaError_t e = growStaging(s->stTables, s->stTablesBytes, ((size_t)frame->width + frame->height) * sizeof(float));
+    if (e == cudaSuccess) e = growStaging(s->stHits, s->stHitsBytes, slots * sizeof(dodrt_hit));
+    if (e == cudaSuccess) e = growStaging(s->stVis, s->stVisBytes, slots);
+    if (e != cudaSuccess) return fail(DODRT_E_CUDA, "dodrt_trace_shadow staging: %s", cudaGetErrorString(e));
+    float *d_tables = s->stTables;
+    dodrt_hit *d_hits = s->stHits;
+    uint8_t *d_vis = s->stVis;
+    e = cudaMemcpyAsync(d_tables, xs, frame->width * sizeof(float), cudaMemcpyHostToDevice, st);
     if (e == cudaSuccess) {
         e = cudaMemcpyAsync(d_tables + frame->width, ys, frame->height * sizeof(float), cudaMemcpyHostToDevice, st);
     }
@@ -1478,9 +1480,6 @@ try {
         rc = launchFrame(s, kModeShadow, frame, d_tables, d_tables + frame->width, d_hits, light, d_vis, st);
         if (rc == DODRT_OK) e = cudaMemcpyAsync(visible, d_vis, slots, cudaMemcpyDeviceToHost, st);
     }
-    if (d_tables) cudaFreeAsync(d_tables, st);
-    if (d_hits) cudaFreeAsync(d_hits, st);
-    if (d_vis) cudaFreeAsync(d_vis, st);
     cudaError_t es = cudaStreamSynchronize(st);
     if (rc != DODRT_OK) return rc;
     if (e == cudaSuccess) e = es;
