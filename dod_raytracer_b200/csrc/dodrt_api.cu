@@ -1659,6 +1659,16 @@ static int renderOnDevice(dodrt_scene *s, const dodrt_frame *frame, const float 
     if (e == cudaSuccess) {
         e = cudaMemcpyAsync(d_tables + frame->width, ys, frame->height * sizeof(float), cudaMemcpyHostToDevice, st);
     }
+    // scratch of the per-bounce spatial sort (DODRT_RENDER_SORT=0 switches it off; rays < 2^32)
+    const char *sortEnv = std::getenv("DODRT_RENDER_SORT");
+    const bool sortBounces = (!sortEnv || std::atoi(sortEnv) != 0) && num_lights != 0 && depth > 1 && n < 0xFFFFFFFFull;
+    uint32_t *bins = nullptr, *order = nullptr;
+    const char *cellEnv = std::getenv("DODRT_RENDER_CELL_BITS");
+    const uint32_t cellBits = cellEnv ? (uint32_t)std::min(7, std::max(4, std::atoi(cellEnv))) : 5u;
+    const char *sortFromEnv = std::getenv("DODRT_RENDER_SORT_FROM");
+    const uint32_t sortFrom = sortFromEnv ? (uint32_t)std::max(0, std::atoi(sortFromEnv)) : 1u;
+    if (sortBounces && e == cudaSuccess) e = cudaMallocFromPoolAsync(&bins, sizeof(uint32_t) * (2u << (3u * cellBits)), s->pool, st);
+    if (sortBounces && e == cudaSuccess) e = cudaMallocFromPoolAsync(&order, sizeof(uint32_t) * n, s->pool, st);
     rp.xs = d_tables;
     rp.ys = d_tables ? d_tables + frame->width : nullptr;
     rp.rgb = d_rgb;
@@ -1674,10 +1684,18 @@ static int renderOnDevice(dodrt_scene *s, const dodrt_frame *frame, const float 
         p.hits = rp.hits;
         // bounce passes: incoherent rays, long tails (dragon as-is frame 182 -> 166 ms with donation)
         p.variant = resolve_variant(s->variant, s->cfg[kDonateVariant][kModeRays], p.count, true, s->dev.num_nodes >= kBigTreeNodes);
+        // bounce k >= 2 starts where bounce k-1 hit: the cell order of those hit points is the order of these origins
+        if (k >= sortFrom + 1 && sortBounces && order) p.ray_order = order;
         p.counter = nextCounter(s);
         e = launchTraceOn(s, kModeRays, p, st); // closest-hit chain, main.cpp:314-321
         if (e == cudaSuccess) s->launches.fetch_add(1);
         if (num_lights && e == cudaSuccess) { // canSeeLight for every light (main.cpp:226): one launch, light-major
+            // from the second bounce on the hit points of neighbouring pixels are scattered: walk them cell by cell
+            if (k >= sortFrom && sortBounces && order) {
+                e = launch_render_sort(rp, cellBits, bins, order, st);
+                if (e == cudaSuccess) s->launches.fetch_add(3);
+                p.ray_order = order;
+            }
             p.counter = nextCounter(s);
             p.visible = rp.visible;
             p.num_lights = num_lights;
@@ -1701,6 +1719,8 @@ static int renderOnDevice(dodrt_scene *s, const dodrt_frame *frame, const float 
     if (rp.hits) cudaFreeAsync(rp.hits, st);
     if (rp.visible) cudaFreeAsync(rp.visible, st);
     if (rp.accum) cudaFreeAsync(rp.accum, st);
+    if (bins) cudaFreeAsync(bins, st);
+    if (order) cudaFreeAsync(order, st);
     if (e != cudaSuccess) return fail(DODRT_E_CUDA, "dodrt_render: %s", cudaGetErrorString(e));
     return DODRT_OK;
 }

@@ -574,14 +574,21 @@ __global__ void __launch_bounds__(128, VARIANT >= kDonateVariant ? 5 : DODRT_MIN
             // (hits[i]) to p.light; visible[i] = 1 iff there was a hit and nothing blocks the light
             float so[3] = {0.0f, 0.0f, 0.0f}, sd[3] = {0.0f, 0.0f, 1.0f}, sclip = 0.0f;
             bool cast = false;
+            uint64_t outItem = item;
             if (inRange) {
                 // all lights of a bounce in one launch: item = light * rays_per_light + ray
                 uint64_t ray = item;
                 float light3[3] = {p.light[0], p.light[1], p.light[2]};
+                uint64_t lightBase = 0;
                 if (p.num_lights > 1u) {
                     const uint32_t l = (uint32_t)(item / p.rays_per_light);
-                    ray = item - (uint64_t)l * p.rays_per_light;
+                    lightBase = (uint64_t)l * p.rays_per_light;
+                    ray = item - lightBase;
                     light3[0] = p.lights[l][0], light3[1] = p.lights[l][1], light3[2] = p.lights[l][2];
+                }
+                if (p.ray_order != nullptr) { // spatially sorted processing order; the result stays at the ray's own index
+                    ray = __ldg(p.ray_order + ray);
+                    outItem = lightBase + ray;
                 }
                 const float4 *src = reinterpret_cast<const float4 *>(p.rays + ray);
                 const float4 a = src[0], b = src[1];
@@ -594,16 +601,18 @@ __global__ void __launch_bounds__(128, VARIANT >= kDonateVariant ? 5 : DODRT_MIN
             }
             Hit h;
             bool donated = false;
-            const bool blocked = query<VARIANT>(p.scene, p.classes, cast, so, sd, true, sclip, h, &p, kFinishVisible, item, &donated);
+            const bool blocked = query<VARIANT>(p.scene, p.classes, cast, so, sd, true, sclip, h, &p, kFinishVisible, outItem, &donated);
             if (inRange && !donated) {
-                p.visible[item] = (cast && !blocked) ? 1 : 0;
+                p.visible[outItem] = (cast && !blocked) ? 1 : 0;
             }
         } else if (MODE == kModeRays) {
             float o[3] = {0.0f, 0.0f, 0.0f}, d[3] = {0.0f, 0.0f, 1.0f};
             float clip = 0.0f;
             bool any = false, skip = false;
+            // optional processing order (dodrt_render: the cells of the previous bounce's hit points = these rays' origins)
+            const uint64_t idx = (inRange && p.ray_order != nullptr) ? (uint64_t)__ldg(p.ray_order + item) : item;
             if (inRange) {
-                const float4 *src = reinterpret_cast<const float4 *>(p.rays + item);
+                const float4 *src = reinterpret_cast<const float4 *>(p.rays + idx);
                 const float4 a = __ldg(src), b = __ldg(src + 1);
                 o[0] = a.x, o[1] = a.y, o[2] = a.z;
                 d[0] = a.w, d[1] = b.x, d[2] = b.y;
@@ -614,14 +623,14 @@ __global__ void __launch_bounds__(128, VARIANT >= kDonateVariant ? 5 : DODRT_MIN
             Hit h;
             bool donated = false;
             const bool found = query<VARIANT>(p.scene, p.classes, inRange && !skip, o, d, any, clip, h, &p,
-                                              any ? kFinishAnyRecord : kFinishRecord, item, &donated);
+                                              any ? kFinishAnyRecord : kFinishRecord, idx, &donated);
             if (inRange && !donated) {
                 if (any) { // any-hit defines only hit/miss
                     h.t = clip;
                     h.prim = found ? 0u : DODRT_MISS;
                     h.u = h.v = 0.0f;
                 }
-                reinterpret_cast<float4 *>(p.hits)[item] = make_float4(h.t, __uint_as_float(h.prim), h.u, h.v);
+                reinterpret_cast<float4 *>(p.hits)[idx] = make_float4(h.t, __uint_as_float(h.prim), h.u, h.v);
             }
         } else {
             uint32_t col = 0, row = 0;

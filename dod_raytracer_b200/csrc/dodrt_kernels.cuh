@@ -73,6 +73,9 @@ struct TraceParams {
     uint32_t num_lights;
     float lights[16][3];
     uint64_t rays_per_light;
+    // kModeShadowRays, optional: process the rays in this order (ray = ray_order[position]); results stay indexed by ray.
+    // dodrt_render sorts the hit points of a bounce into spatial cells so that a warp's 32 shadow rays start close together
+    const uint32_t *ray_order;
     uint64_t visible_light_stride;
     uint64_t shadow_count; // count * num_lights
     uint32_t *tile_done;
@@ -134,6 +137,9 @@ struct RenderParams {
 cudaError_t launch_render_init(const RenderParams &p, cudaStream_t stream);
 cudaError_t launch_render_shade(const RenderParams &p, uint32_t bounce, cudaStream_t stream);
 cudaError_t launch_render_finish(const RenderParams &p, cudaStream_t stream);
+// Spatial order of a bounce's hit points for its shadow passes: order[k] = k-th ray in cell order (counting sort over the
+// (1 << bits)^3 Morton cells of the room, 4 <= bits <= 7; `bins` = 2 << (3 * bits) words of scratch)
+cudaError_t launch_render_sort(const RenderParams &p, uint32_t bits, uint32_t *bins, uint32_t *order, cudaStream_t stream);
 
 // Multi-GPU: gathered per-rank compact results -> row-major frame (one thread per pixel).
 cudaError_t launch_assemble(const dodrt_frame &frame, uint32_t tiles_x, const dodrt_hit *compactHits,

@@ -222,7 +222,98 @@ __global__ void render_finish_kernel(const RenderParams p)
     }
 }
 
+// ---- spatial order of a bounce's hit points (counting sort over Morton cells of the room) ----------------------------
+// After the first bounce the rays of neighbouring pixels have scattered: a warp's 32 shadow rays start all over the scene
+// and share no kd nodes or lanes (bounces 6-10 of the dragon frame: 1.2 Grays/s against 4 for the first).  Shadow rays of
+// one light that START close together stay together, so the hit points are binned into (1 << bits)^3 Morton cells of the scene
+// box (the six planes of the reference's room span [-5, 5]^3; anything outside is clamped) and the shadow passes of the
+// bounce walk the rays cell by cell.  Only the processing order changes: every ray's result lands at its own index.
+__device__ __forceinline__ uint32_t spread10(uint32_t v) // up to 10 bits -> every third bit
+{
+    v &= 1023u;
+    v = (v | (v << 16)) & 0x030000FFu;
+    v = (v | (v << 8)) & 0x0300F00Fu;
+    v = (v | (v << 4)) & 0x030C30C3u;
+    v = (v | (v << 2)) & 0x09249249u;
+    return v;
+}
+
+// cell of slot `pix`'s hit point: Morton code of a (1 << bits)^3 grid over [-5, 5]^3, or the last cell for a ray that casts
+// no shadow ray (dead or missed)
+__device__ __forceinline__ uint32_t render_cell(const RenderParams &p, uint64_t pix, uint32_t bits)
+{
+    const uint32_t cells = 1u << (3u * bits);
+    const float4 *ray = reinterpret_cast<const float4 *>(p.rays + pix);
+    const float4 r0 = ray[0], r1 = ray[1];
+    const float4 h = reinterpret_cast<const float4 *>(p.hits)[pix];
+    if ((__float_as_uint(r1.w) & DODRT_RAY_SKIP) || __float_as_uint(h.y) == DODRT_MISS) {
+        return cells - 1u;
+    }
+    const float P[3] = {r0.x + r0.w * h.x, r0.y + r1.x * h.x, r0.z + r1.y * h.x};
+    const float scale = (float)(1u << bits) * 0.1f, top = (float)((1u << bits) - 1u);
+    uint32_t c[3];
+#pragma unroll
+    for (int k = 0; k < 3; k++) {
+        const float g = (P[k] + 5.0f) * scale; // [-5, 5] -> [0, 2^bits)
+        c[k] = g > 0.0f ? (g < top ? (uint32_t)g : (uint32_t)top) : 0u;
+    }
+    return spread10(c[0]) | (spread10(c[1]) << 1) | (spread10(c[2]) << 2);
+}
+
+__global__ void render_bin_count_kernel(const RenderParams p, uint32_t bits, uint32_t *bins)
+{
+    const uint64_t pix = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (pix < p.slots) {
+        atomicAdd(bins + render_cell(p, pix, bits), 1u);
+    }
+}
+
+// exclusive prefix sum of the `cells` counts into bins[cells ...] (one block, 1024 threads x cells / 1024 cells each)
+__global__ void render_bin_scan_kernel(uint32_t *bins, uint32_t cells)
+{
+    __shared__ uint32_t partial[1024];
+    const uint32_t t = threadIdx.x, per = cells / 1024u;
+    uint32_t sum = 0;
+    for (uint32_t k = 0; k < per; k++) {
+        sum += bins[t * per + k];
+    }
+    partial[t] = sum;
+    __syncthreads();
+    for (uint32_t off = 1; off < 1024u; off <<= 1) { // Hillis-Steele inclusive scan
+        const uint32_t v = t >= off ? partial[t - off] : 0u;
+        __syncthreads();
+        partial[t] += v;
+        __syncthreads();
+    }
+    uint32_t run = partial[t] - sum;
+    for (uint32_t k = 0; k < per; k++) {
+        const uint32_t c = bins[t * per + k];
+        bins[cells + t * per + k] = run;
+        run += c;
+    }
+}
+
+__global__ void render_bin_scatter_kernel(const RenderParams p, uint32_t bits, uint32_t *bins, uint32_t *order)
+{
+    const uint64_t pix = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (pix < p.slots) {
+        order[atomicAdd(bins + (1u << (3u * bits)) + render_cell(p, pix, bits), 1u)] = (uint32_t)pix;
+    }
+}
+
 } // namespace
+
+cudaError_t launch_render_sort(const RenderParams &p, uint32_t bits, uint32_t *bins, uint32_t *order, cudaStream_t stream)
+{
+    const uint64_t n = p.slots;
+    const uint32_t cells = 1u << (3u * bits);
+    cudaError_t e = cudaMemsetAsync(bins, 0, sizeof(uint32_t) * cells, stream);
+    if (e != cudaSuccess) return e;
+    render_bin_count_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(p, bits, bins);
+    render_bin_scan_kernel<<<1, 1024, 0, stream>>>(bins, cells);
+    render_bin_scatter_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(p, bits, bins, order);
+    return cudaGetLastError();
+}
 
 cudaError_t launch_render_init(const RenderParams &p, cudaStream_t stream)
 {

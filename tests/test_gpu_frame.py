@@ -272,6 +272,15 @@ def test_render_tile_split_and_multi_gpu():
     with hs.upload(0, shading=True) as g:
         want = g.render(capi.Frame.make(w, h, classes=ALL), xs, ys, workloads.REFERENCE_LIGHTS, depth)
         assert want.mean() > 10
+        # the per-bounce spatial sort of the hit points only changes the order in which rays are traced
+        for knobs in ({"DODRT_RENDER_SORT": "0"}, {"DODRT_RENDER_CELL_BITS": "6", "DODRT_RENDER_SORT_FROM": "0"}):
+            os.environ.update(knobs)
+            try:
+                other = g.render(capi.Frame.make(w, h, classes=ALL), xs, ys, workloads.REFERENCE_LIGHTS, depth)
+            finally:
+                for k in knobs:
+                    os.environ.pop(k, None)
+            assert other.tobytes() == want.tobytes(), knobs
         for world, tile in ((3, (32, 32)), (4, (16, 8))):
             full = np.zeros((h * w, 3), np.uint8)
             comp = np.zeros((h * w, 3), np.uint8)
