@@ -398,11 +398,41 @@ int launchFrame(dodrt_scene *s, TraceMode mode, const dodrt_frame *frame, const 
     cudaError_t le = launchTraceOn(s, mode, p, stream);
 #ifdef DODRT_TIMELINE
     { // debug build: where does a pass spend its time?  (start, first warp out of work, last warp busy, last helper gone)
-        unsigned long long tl[4];
+        unsigned long long tl[8];
         cudaStreamSynchronize(stream);
-        cudaMemcpy(tl, p.counter + 24, 32, cudaMemcpyDeviceToHost);
-        std::fprintf(stderr, "timeline mode %d variant %d count %llu: first-idle %+.1f us, last-busy %+.1f us, end %+.1f us\n", (int)mode,
-                     p.variant, (unsigned long long)p.count, (tl[1] - tl[0]) * 1e-3, (tl[2] - tl[0]) * 1e-3, (tl[3] - tl[0]) * 1e-3);
+        cudaMemcpy(tl, p.counter + 24, 64, cudaMemcpyDeviceToHost);
+        unsigned long long served = 0;
+        cudaMemcpy(&served, p.counter + kDonateServed, 8, cudaMemcpyDeviceToHost);
+        if (served) {
+            std::fprintf(stderr, "   resumed rays %llu: node steps %.1f per ray at %.0f cycles each, leaf steps (128 slots) %.1f per ray at %.0f cycles each\n",
+                         served, (double)tl[6] / served, tl[6] ? (double)tl[4] / tl[6] : 0.0,
+                         (double)tl[7] / served, tl[7] ? (double)tl[5] / tl[7] : 0.0);
+        }
+        unsigned long long ex[2] = {0, 0}; // [21] warps, [22] sum of their main-loop exit times
+        cudaMemcpy(ex, p.counter + 21, 16, cudaMemcpyDeviceToHost);
+        std::fprintf(stderr, "timeline mode %d variant %d count %llu: first-idle %+.1f us, mean main-loop exit %+.1f us (%llu warps), last-busy %+.1f us, end %+.1f us; resumed rays took %.1f us per warp\n",
+                     (int)mode, p.variant, (unsigned long long)p.count, (tl[1] - tl[0]) * 1e-3,
+                     ex[0] ? ((double)ex[1] / ex[0] - (double)(tl[0] & 0xFFFFFFFFFull)) * 1e-3 : 0.0, ex[0], (tl[2] - tl[0]) * 1e-3, (tl[3] - tl[0]) * 1e-3,
+                     ex[0] ? (double)(tl[4] + tl[5]) / ex[0] / 1.92e3 : 0.0);
+        { // histograms over 16-us bins since the kernel started: warps leaving their main loop; donations (events, rays given, rays kept)
+            static unsigned long long exits[8192], dons[1 << 16];
+            unsigned int nd = 0, pollsEmpty = 0;
+            timeline_fetch(exits, dons, &nd, &pollsEmpty);
+            unsigned hExit[48] = {0}, hDon[48] = {0}, hGiven[48] = {0}, hKept[48] = {0};
+            for (int i = 0; i < 8192; i++) {
+                if (exits[i] >= tl[0]) hExit[std::min<unsigned long long>((exits[i] - tl[0]) / 16000ull, 47ull)]++;
+            }
+            const unsigned long long t0m = tl[0] & ((1ull << 52) - 1ull);
+            for (unsigned i = 0; i < std::min(nd, 1u << 16); i++) {
+                const unsigned long long t = dons[i] >> 12;
+                const unsigned long long b = t >= t0m ? std::min<unsigned long long>((t - t0m) / 16000ull, 47ull) : 47ull;
+                hDon[b]++, hGiven[b] += (unsigned)((dons[i] >> 6) & 63u), hKept[b] += (unsigned)(dons[i] & 63u);
+            }
+            std::fprintf(stderr, "   %u donations, %u polls found no waiting helper\n   bin(16us): exits | donations given kept\n", nd, pollsEmpty);
+            for (int b = 0; b < 48; b++) {
+                if (hExit[b] | hDon[b]) std::fprintf(stderr, "   %3d: %5u | %5u %5u %5u\n", b, hExit[b], hDon[b], hGiven[b], hKept[b]);
+            }
+        }
     }
 #endif
     if (p.tile_order) {

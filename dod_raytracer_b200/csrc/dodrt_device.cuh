@@ -236,6 +236,30 @@ __device__ __forceinline__ bool triangle_may_hit(float Ax, float Ay, float Az, f
     return (ad > 0.0f) & !sign_differs_or_zero(a, det) & !(fabsf(a) > ad * 1.00001f);
 }
 
+// All conservative stages of triangle_test_fast for one triangle, branch-free (det, u, v, u + v and the sign of t on
+// the un-divided numerators): a triangle that fails is rejected by the reference's own compares for sure; what passes
+// is, up to the last-bit margins, a real intersection in front of the origin.  Used where ONE warp works on one ray and
+// the only instruction-level parallelism is between the slots a thread tests (dodrt_donate.inl).
+__device__ __forceinline__ bool triangle_may_hit_full(float Ax, float Ay, float Az, float ABx, float ABy, float ABz, float ACx,
+                                                      float ACy, float ACz, const float o[3], const float d[3])
+{
+    float px = d[1] * ACz - d[2] * ACy;
+    float py = d[2] * ACx - d[0] * ACz;
+    float pz = d[0] * ACy - d[1] * ACx;
+    float det = dot3(px, py, pz, ABx, ABy, ABz);
+    float tx = o[0] - Ax, ty = o[1] - Ay, tz = o[2] - Az;
+    float a = dot3(tx, ty, tz, px, py, pz);
+    float qx = ty * ABz - tz * ABy;
+    float qy = tz * ABx - tx * ABz;
+    float qz = tx * ABy - ty * ABx;
+    float b = dot3(d[0], d[1], d[2], qx, qy, qz);
+    float c = dot3(ACx, ACy, ACz, qx, qy, qz);
+    const float ad = fabsf(det), lim = ad * 1.00001f;
+    // exactly the early-out predicates of triangle_test_fast, in its polarity (NaN numerators fall through to the exact test)
+    return (ad > 0.0f) & !sign_differs_or_zero(a, det) & !(fabsf(a) > lim) & !sign_differs_or_zero(b, det) &
+           !(fabsf(a) + fabsf(b) > lim) & !sign_differs_or_zero(c, det);
+}
+
 // Four consecutive triangle slots (4h .. 4h+3) of one SoA lane: 9 x LDG.128, a branch-free first stage
 // for all four (independent dependency chains), and the full test -- in slot order, against the running
 // clip -- only for the survivors.  Returns true when at least one triangle was accepted.

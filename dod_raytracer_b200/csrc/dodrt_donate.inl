@@ -156,6 +156,13 @@ __device__ __forceinline__ void donate_live_rays(const TraceParams &p, uint32_t 
         base = atomicAdd(p.counter + kDonateTail, (unsigned long long)n);
     }
     base = __shfl_sync(0xffffffffu, base, 0);
+#ifdef DODRT_TIMELINE
+    if (lane == 0) {
+        unsigned long long t;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+        g_tlDonation[atomicAdd(&g_tlDonations, 1u) & 0xFFFFu] = (t << 12) | ((unsigned long long)n << 6) | (unsigned long long)(__popc(candidates) - n);
+    }
+#endif
     if (give) {
         SuspendedRay r;
         const uint32_t flags = (any ? kFlagAny : 0u) | (found ? kFlagFound : 0u);
@@ -216,6 +223,8 @@ __device__ __forceinline__ bool answer_decided(const TraceParams &p, uint32_t ki
 }
 
 // Helper side: the whole warp resumes the ray (or the piece of an any-hit ray) in `slot` and writes its result.
+__device__ __forceinline__ float pick4(const float4 &q, int j) { return j == 0 ? q.x : j == 1 ? q.y : j == 2 ? q.z : q.w; }
+
 __device__ __forceinline__ void resume_ray(const TraceParams &p, uint32_t slot)
 {
     const DeviceScene &s = p.scene;
@@ -253,17 +262,62 @@ __device__ __forceinline__ void resume_ray(const TraceParams &p, uint32_t slot)
         stackTmax[i] = __uint_as_float(__ldcg(stk + 3 * i + 2));
     }
     uint32_t sincePoll = 0;
+#ifdef DODRT_TIMELINE
+    unsigned long long tlNode = 0, tlLeaf = 0, tlNodeSteps = 0, tlLeafSteps = 0;
+#endif
     while (st.live) { // warp-uniform: every lane holds the same state
+#ifdef DODRT_TIMELINE
+        const long long tl0 = clock64();
+        const bool tlIsLeaf = st.triCur < st.triEnd;
+#endif
         if (st.triCur < st.triEnd) {
-            const uint32_t tri = st.triCur + lane;
-            bool acc = false;
+            // 128 triangle slots per step: lane L tests slots triCur + 4L .. 4L + 3, which are four adjacent columns of ONE
+            // SoA triangle lane (triangle.h:33-44: 9 rows of 8 floats), so nine 16-byte loads fetch all four triangles
+            // and a leaf of up to 16 triangle lanes is one step (round 1 tested 32 slots per step with nine 4-byte loads
+            // per lane: 8.7 steps per resumed ray against 4.0 now; profiles/r02_donation_fork.txt, section 6).
+            const uint32_t first = st.triCur + 4u * lane; // triCur, triEnd are multiples of 8: all four slots are in or out
+            const bool in = first < st.triEnd;
+            float4 r[9];
+#pragma unroll
+            for (int k = 0; k < 9; k++) {
+                r[k] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+            }
+            if (in) {
+                const float4 *base = reinterpret_cast<const float4 *>(reinterpret_cast<const float *>(s.lanes4) +
+                                                                      (size_t)(first >> 3) * 72 + (first & 7u));
+#pragma unroll
+                for (int k = 0; k < 9; k++) {
+                    r[k] = __ldg(base + 2 * k);
+                }
+            }
+            // First stage for the four slots at once: every conservative compare of triangle_test_fast, branch-free, four
+            // independent dependency chains (a warp that works on one ray has no other source of instruction-level
+            // parallelism).  The exact test, with its division, runs only for what is almost certainly a hit, lowest
+            // slot first, and strict `<` keeps the lower slot on a tie (triangle.cpp:133).  All slots are compared
+            // with the clip at the START of the step, then reduced with the lexicographic (t, slot) minimum: what the
+            // reference's running clip leaves behind.
+            uint32_t m = 0;
+            if (in) {
+                m = (uint32_t)triangle_may_hit_full(r[0].x, r[1].x, r[2].x, r[3].x, r[4].x, r[5].x, r[6].x, r[7].x, r[8].x, o, d) |
+                    ((uint32_t)triangle_may_hit_full(r[0].y, r[1].y, r[2].y, r[3].y, r[4].y, r[5].y, r[6].y, r[7].y, r[8].y, o, d) << 1) |
+                    ((uint32_t)triangle_may_hit_full(r[0].z, r[1].z, r[2].z, r[3].z, r[4].z, r[5].z, r[6].z, r[7].z, r[8].z, o, d) << 2) |
+                    ((uint32_t)triangle_may_hit_full(r[0].w, r[1].w, r[2].w, r[3].w, r[4].w, r[5].w, r[6].w, r[7].w, r[8].w, o, d) << 3);
+            }
             float t = 0.0f, u = 0.0f, v = 0.0f;
-            if (tri < st.triEnd) {
-                const float *base = reinterpret_cast<const float *>(s.lanes4) + (size_t)(tri >> 3) * 72 + (tri & 7u);
-                const float4 q0 = make_float4(__ldg(base), __ldg(base + 8), __ldg(base + 16), __ldg(base + 24));
-                const float4 q1 = make_float4(__ldg(base + 32), __ldg(base + 40), __ldg(base + 48), __ldg(base + 56));
-                const float4 q2 = make_float4(__ldg(base + 64), 0.0f, 0.0f, 0.0f);
-                acc = triangle_test_fast(q0, q1, q2, o, d, clip, t, u, v);
+            uint32_t slotId = first;
+            bool acc = false;
+            while (m != 0u) {
+                const int j = __ffs((int)m) - 1;
+                m &= m - 1u;
+                const float4 q0 = make_float4(pick4(r[0], j), pick4(r[1], j), pick4(r[2], j), pick4(r[3], j));
+                const float4 q1 = make_float4(pick4(r[4], j), pick4(r[5], j), pick4(r[6], j), pick4(r[7], j));
+                const float4 q2 = make_float4(pick4(r[8], j), 0.0f, 0.0f, 0.0f);
+                float tj = 0.0f, uj = 0.0f, vj = 0.0f;
+                if (triangle_test_fast(q0, q1, q2, o, d, clip, tj, uj, vj) && (!acc || tj < t)) {
+                    t = tj, u = uj, v = vj;
+                    slotId = first + (uint32_t)j;
+                    acc = true;
+                }
             }
             const unsigned accMask = __ballot_sync(0xffffffffu, acc);
             if (accMask != 0u) {
@@ -272,16 +326,18 @@ __device__ __forceinline__ void resume_ray(const TraceParams &p, uint32_t slot)
                 for (uint32_t off = 16; off != 0u; off >>= 1) {
                     best = fminf(best, __shfl_xor_sync(0xffffffffu, best, off));
                 }
-                const unsigned winners = __ballot_sync(0xffffffffu, acc && t == best);
-                const uint32_t src = (uint32_t)__ffs((int)winners) - 1u; // lowest slot id among equal t
+                // lowest slot id among equal t = what the reference's slot-by-slot loop leaves behind
+                const uint32_t winSlot = __reduce_min_sync(0xffffffffu, (acc && t == best) ? slotId : 0xFFFFFFFFu);
+                const unsigned winners = __ballot_sync(0xffffffffu, acc && t == best && slotId == winSlot);
+                const uint32_t src = (uint32_t)__ffs((int)winners) - 1u;
                 clip = best;
                 hit.t = best;
-                hit.prim = (DODRT_KIND_TRIANGLE << DODRT_KIND_SHIFT) | (st.triCur + src);
+                hit.prim = (DODRT_KIND_TRIANGLE << DODRT_KIND_SHIFT) | winSlot;
                 hit.u = __shfl_sync(0xffffffffu, u, src);
                 hit.v = __shfl_sync(0xffffffffu, v, src);
                 found = true;
             }
-            st.triCur = st.triCur + 32u < st.triEnd ? st.triCur + 32u : st.triEnd;
+            st.triCur = st.triCur + 128u < st.triEnd ? st.triCur + 128u : st.triEnd;
             if (any && found) {
                 st.live = false; // kdtree.cpp:338-341
             } else if (st.triCur == st.triEnd) {
@@ -290,6 +346,15 @@ __device__ __forceinline__ void resume_ray(const TraceParams &p, uint32_t slot)
         } else {
             node_step(s, st, o, d, clip, stackNode, stackTmin, stackTmax);
         }
+#ifdef DODRT_TIMELINE
+        if (tlIsLeaf) {
+            tlLeaf += (unsigned long long)(clock64() - tl0);
+            tlLeafSteps++;
+        } else {
+            tlNode += (unsigned long long)(clock64() - tl0);
+            tlNodeSteps++;
+        }
+#endif
 #ifdef DODRT_EXPERIMENTS
         // ---- work splitting (any-hit rays only): give the oldest stack entries to helpers that wait without a ray
         if (any && st.live && s.fork_poll != 0u && ++sincePoll >= s.fork_poll) {
@@ -363,6 +428,14 @@ __device__ __forceinline__ void resume_ray(const TraceParams &p, uint32_t slot)
 #endif // DODRT_EXPERIMENTS (work splitting)
     }
     (void)sincePoll;
+#ifdef DODRT_TIMELINE
+    if (lane == 0) { // debug build: where does a resumed ray spend its cycles?  [28] node cycles [29] leaf cycles [30] node steps [31] leaf steps
+        atomicAdd(p.counter + 28, tlNode);
+        atomicAdd(p.counter + 29, tlLeaf);
+        atomicAdd(p.counter + 30, tlNodeSteps);
+        atomicAdd(p.counter + 31, tlLeafSteps);
+    }
+#endif
     if (lane == 0) {
         if (forked) { // pieces of a forked ray only ever turn the optimistic answer into "blocked" / "hit"
             if (found) {

@@ -331,6 +331,14 @@ __device__ __forceinline__ void leaf_step_coop(const DeviceScene &s, TreeState &
     }
 }
 
+#ifdef DODRT_TIMELINE
+// debug build only: per-warp exit times and per-donation (time, rays given, live rays kept) records of the LAST launch
+__device__ unsigned long long g_tlExit[8192];
+__device__ unsigned long long g_tlDonation[1 << 16];
+__device__ unsigned int g_tlDonations;
+__device__ unsigned int g_tlPollsEmpty;
+#endif
+
 #include "dodrt_donate.inl"
 
 template <bool SOA, bool SHARE, bool PACKED, bool DONATE, bool COMPACT = false>
@@ -389,6 +397,9 @@ __device__ __forceinline__ bool kdtree_query_voted(const DeviceScene &s, bool en
         }
         // do idle warps wait for rays?
         const uint32_t want = (p->donate_slots != nullptr && allowDonate) ? donate_poll(*p) : 0u;
+#ifdef DODRT_TIMELINE
+        if (want == 0u && (threadIdx.x & 31u) == 0u) atomicAdd(&g_tlPollsEmpty, 1u);
+#endif
         if (want != 0u) {
             donate_live_rays(*p, want, st, o, d, any, clip, hit, found, fin, stackNode, stackTmin, stackTmax, *donated);
         }
@@ -689,6 +700,9 @@ __global__ void __launch_bounds__(128, VARIANT >= kDonateVariant ? 5 : DODRT_MIN
         asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
         atomicMin(p.counter + 25, t); // first warp out of work
         atomicMax(p.counter + 26, t); // last warp out of its main loop
+        atomicAdd(p.counter + 22, t & 0xFFFFFFFFFull); // (sum over warps, low 36 bits: the average time a warp leaves its main loop)
+        atomicAdd(p.counter + 21, 1ull);
+        g_tlExit[(blockIdx.x * blockDim.x + threadIdx.x) >> 5 & 8191u] = t;
     }
 #endif
 #ifndef DBG_NOHELPER
@@ -1155,6 +1169,21 @@ size_t donation_queue_bytes(const LaunchConfig &cfg)
     const size_t readyBytes = (cap * sizeof(uint32_t) + 255) & ~(size_t)255;
     return readyBytes + cap * kDonateSlotWords * sizeof(uint32_t);
 }
+
+#ifdef DODRT_TIMELINE
+void timeline_fetch(unsigned long long *exits, unsigned long long *donations, unsigned int *numDonations, unsigned int *pollsEmpty)
+{
+    cudaMemcpyFromSymbol(exits, g_tlExit, sizeof(unsigned long long) * 8192);
+    cudaMemcpyFromSymbol(donations, g_tlDonation, sizeof(unsigned long long) * (1 << 16));
+    cudaMemcpyFromSymbol(numDonations, g_tlDonations, sizeof(unsigned int));
+    cudaMemcpyFromSymbol(pollsEmpty, g_tlPollsEmpty, sizeof(unsigned int));
+    const unsigned int zero = 0;
+    cudaMemcpyToSymbol(g_tlDonations, &zero, sizeof(zero));
+    cudaMemcpyToSymbol(g_tlPollsEmpty, &zero, sizeof(zero));
+    static unsigned long long zeros[8192];
+    cudaMemcpyToSymbol(g_tlExit, zeros, sizeof(zeros));
+}
+#endif
 
 cudaError_t launch_trace(TraceMode mode, const TraceParams &params, const LaunchConfig &cfg, cudaStream_t stream,
                          cudaMemPool_t pool, void *persistentQueue, uint32_t epoch)

@@ -110,6 +110,9 @@ constexpr uint32_t kBigTreeNodes = 8192;
 // allocated, used with a fresh non-zero `epoch` per launch -- nothing to clear), or a per-launch allocation from `pool`
 // (stream-ordered, ready words zeroed on the stream); neither = no donation.
 size_t donation_queue_bytes(const LaunchConfig &cfg);
+#ifdef DODRT_TIMELINE
+void timeline_fetch(unsigned long long *exits, unsigned long long *donations, unsigned int *numDonations, unsigned int *pollsEmpty);
+#endif
 cudaError_t launch_trace(TraceMode mode, const TraceParams &p, const LaunchConfig &cfg, cudaStream_t stream,
                          cudaMemPool_t pool = nullptr, void *queue = nullptr, uint32_t epoch = 0);
 
