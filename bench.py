@@ -271,9 +271,9 @@ def roofline_of(w, world, shadow_rays, kernel_ms, per_pass_ms, sizes, nl, clocks
             "note": "no ncu counters for this workload/kernel in profiles/traffic.json: HBM view against compulsory bytes only"}
     prof = os.path.join(ROOT, "profiles", "traffic.json")
     hw = None
-    if os.path.exists(prof) and world == 1:
-        try:
-            hw = json.load(open(prof)).get(w.name, {}).get(name)
+    if os.path.exists(prof):
+        try:  # N > 1: the counters of rank 0's share of an N-way split, when that split was captured
+            hw = json.load(open(prof)).get(w.name if world == 1 else f"{w.name}@{world}", {}).get(name)
         except Exception:
             hw = None
     if hw:
@@ -469,7 +469,11 @@ def main():
     prim_ms = [e[0].elapsed_time(e[1]) for e in events]
     shad_ms = [e[1].elapsed_time(e[2]) for e in events]
     total_ms = torch.tensor([sum(step_ms), sum(prim_ms), sum(shad_ms)], device=dev, dtype=torch.float64)
+    rank_ms = [sum(step_ms) / args.steps]
     if world > 1:
+        every = [torch.zeros(1, device=dev, dtype=torch.float64) for _ in range(world)]
+        dist.all_gather(every, total_ms[:1].clone())
+        rank_ms = [float(t.item()) / args.steps for t in every]
         dist.all_reduce(total_ms, op=dist.ReduceOp.MAX)
         lt = torch.tensor([launches], device=dev, dtype=torch.int64)
         dist.all_reduce(lt)
@@ -576,6 +580,7 @@ def main():
             "details": {"shadow_rays": shadow_rays * nl, "triangles": sizes.num_triangles, "kd_nodes": sizes.num_nodes,
                         "tri_lanes": sizes.num_lanes, "tile": args.tile, "parallelism": how,
                         "host_build_s": round(build_s, 2), "upload_s": round(upload_s, 2), "wall_s_timed_region": round(wall, 3),
+                        "rank_ms_per_step": [round(x, 4) for x in rank_ms],
                         "mesh_note": "stand-in geometry: assets/dragon.obj is a missing blob in the reference" if standin else None},
             "e2e": e2e, "gpu_launches": launches, "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu_baseline,
             "parity": parity, "frame_ms": ms_per_step, "reference_frame": reference_frame}
