@@ -618,16 +618,24 @@ template <typename T> cudaError_t growStaging(T *&ptr, size_t &have, size_t need
 }
 
 // `to` waits for what `from` has queued so far; events are pre-created and recycled call after call
-cudaError_t stagingFence(dodrt_scene *s, cudaStream_t from, cudaStream_t to)
+// The next event of the scene's per-call pool (dodrt_scene::stEventsUsed is reset at the start of a host-buffer call).
+cudaError_t stagingEvent(dodrt_scene *s, cudaEvent_t *ev)
 {
     if (s->stEventsUsed == s->stEvents.size()) {
-        cudaEvent_t ev = nullptr;
-        cudaError_t e = cudaEventCreateWithFlags(&ev, cudaEventDisableTiming);
+        cudaEvent_t fresh = nullptr;
+        cudaError_t e = cudaEventCreateWithFlags(&fresh, cudaEventDisableTiming);
         if (e != cudaSuccess) return e;
-        s->stEvents.push_back(ev);
+        s->stEvents.push_back(fresh);
     }
-    cudaEvent_t ev = s->stEvents[s->stEventsUsed++];
-    cudaError_t e = cudaEventRecord(ev, from);
+    *ev = s->stEvents[s->stEventsUsed++];
+    return cudaSuccess;
+}
+
+cudaError_t stagingFence(dodrt_scene *s, cudaStream_t from, cudaStream_t to)
+{
+    cudaEvent_t ev = nullptr;
+    cudaError_t e = stagingEvent(s, &ev);
+    if (e == cudaSuccess) e = cudaEventRecord(ev, from);
     return e == cudaSuccess ? cudaStreamWaitEvent(to, ev, 0) : e;
 }
 
@@ -1582,7 +1590,107 @@ try {
         mHits = mappedHostPointer(hits, pixels * sizeof(dodrt_hit));
         mVis = num_lights ? mappedHostPointer(visible, pixels * num_lights) : nullptr;
     }
-    const bool direct = mHits && (num_lights == 0 || mVis);
+    const bool pinned = mHits && (num_lights == 0 || mVis);
+    // Pinned host frame, default: STAGED BANDS.  The frame is cut into bands of whole pixel rows (tiles as wide as the
+    // frame, or half / a third of it beyond kMaxTileSide), dealt round-robin; every GPU traces its bands into its own
+    // full-frame staging buffer and DMAs each band to the same place of the caller's frame -- contiguous rows, so a band
+    // is one copy -- with the hit records on their way while the shadow pass runs.  DODRT_ZEROCOPY=1 selects the round-2
+    // first form instead (the kernels store into the mapped host frame themselves), which measured slower on this pool:
+    // dragon4k 5.8 / 3.5 / 3.2 / 3.6 ms on 1 / 2 / 4 / 8 GPUs (tests/tools/multi_bench.py).
+    const char *zcEnv = std::getenv("DODRT_ZEROCOPY");
+    const bool direct = pinned && zcEnv && std::atoi(zcEnv) != 0;
+    if (pinned && !direct) {
+        const uint32_t W = frame->width, H = frame->height;
+        const uint32_t tilesX = (W + kMaxTileSide - 1) / kMaxTileSide;
+        const uint32_t tileW = (((W + tilesX - 1) / tilesX) + 7u) & ~7u;
+        uint32_t bandH = (H / (16u * n)) & ~3u; // ~16 bands per GPU: the shares differ by one band at most
+        bandH = bandH < 4u ? 4u : (bandH > 64u ? 64u : bandH);
+        const uint32_t bandsY = (H + bandH - 1) / bandH;
+        const uint64_t totalTiles = (uint64_t)tilesX * bandsY;
+        std::vector<cudaEvent_t> primaryDone(n, nullptr);
+        std::vector<std::vector<cudaEvent_t>> shadowDone(n);
+        std::vector<std::unique_lock<std::mutex>> hostLocks; // released when the call leaves, whichever way
+        hostLocks.reserve(n);
+        for (uint32_t i = 0; i < n; i++) shadowDone[i].reserve(num_lights);
+        cudaError_t e = cudaSuccess;
+        uint32_t locked = 0;
+        // phase 1: every GPU gets its tables and all its launches (asynchronous; the GPUs trace at the same time)
+        for (uint32_t i = 0; i < n && rc == DODRT_OK && e == cudaSuccess; i++) {
+            dodrt_scene *s = m->scenes[i];
+            DeviceGuard guard(s->device);
+            if (!guard.ok) {
+                rc = fail(DODRT_E_CUDA, "cannot select device %d", s->device);
+                break;
+            }
+            hostLocks.emplace_back(s->hostMutex); // persistent staging, like dodrt_trace_frame
+            locked = i + 1;
+            s->stEventsUsed = 0;
+            if (i >= totalTiles) continue;
+            dodrt_frame f = *frame;
+            f.tile_w = tileW, f.tile_h = bandH, f.first_tile = i, f.tile_stride = n, f.compact = 0;
+            e = growStaging(s->stTables, s->stTablesBytes, ((size_t)W + H) * sizeof(float));
+            if (e == cudaSuccess) e = growStaging(s->stHits, s->stHitsBytes, pixels * sizeof(dodrt_hit));
+            if (e == cudaSuccess) e = growStaging(s->stVis, s->stVisBytes, pixels * (size_t)(num_lights ? num_lights : 1));
+            if (e == cudaSuccess) e = cudaMemcpyAsync(s->stTables, xs, W * sizeof(float), cudaMemcpyHostToDevice, s->stream);
+            if (e == cudaSuccess) e = cudaMemcpyAsync(s->stTables + W, ys, H * sizeof(float), cudaMemcpyHostToDevice, s->stream);
+            if (e != cudaSuccess) break;
+            rc = launchFrame(s, kModePrimary, &f, s->stTables, s->stTables + W, s->stHits, nullptr, nullptr, s->stream);
+            if (rc != DODRT_OK) break;
+            e = stagingEvent(s, &primaryDone[i]);
+            if (e == cudaSuccess) e = cudaEventRecord(primaryDone[i], s->stream);
+            for (uint32_t l = 0; l < num_lights && rc == DODRT_OK && e == cudaSuccess; l++) {
+                rc = launchFrame(s, kModeShadow, &f, s->stTables, s->stTables + W, s->stHits, lights + 3 * l, s->stVis + pixels * l,
+                                 s->stream);
+                if (rc != DODRT_OK) break;
+                cudaEvent_t ev = nullptr;
+                e = stagingEvent(s, &ev);
+                if (e == cudaSuccess) e = cudaEventRecord(ev, s->stream);
+                if (e == cudaSuccess) shadowDone[i].push_back(ev);
+            }
+        }
+        // phase 2: the copies, band by band, on every GPU's copy stream behind the pass that produces them.  (One host
+        // thread per GPU instead of the two phases was measured too: 1.87 vs 1.78 ms on 8 GPUs -- the frame is bound by
+        // the D2H traffic into one host frame, ~90 GB/s in aggregate, not by the ~40 CUDA calls per GPU.)
+        auto copyBands = [&](dodrt_scene *s, uint32_t i, const void *src, void *dst, size_t elem) -> cudaError_t {
+            cudaError_t ce = cudaSuccess;
+            for (uint64_t k = i; k < totalTiles && ce == cudaSuccess; k += n) {
+                const uint32_t tx = (uint32_t)(k % tilesX), ty = (uint32_t)(k / tilesX);
+                const uint32_t row0 = ty * bandH, rows = bandH < H - row0 ? bandH : H - row0;
+                const uint32_t col0 = tx * tileW, cols = tileW < W - col0 ? tileW : W - col0;
+                const size_t off = ((size_t)row0 * W + col0) * elem;
+                if (cols == W) {
+                    ce = cudaMemcpyAsync(static_cast<char *>(dst) + off, static_cast<const char *>(src) + off, (size_t)rows * W * elem,
+                                         cudaMemcpyDeviceToHost, s->copyStream);
+                } else {
+                    ce = cudaMemcpy2DAsync(static_cast<char *>(dst) + off, (size_t)W * elem, static_cast<const char *>(src) + off,
+                                           (size_t)W * elem, (size_t)cols * elem, rows, cudaMemcpyDeviceToHost, s->copyStream);
+                }
+            }
+            return ce;
+        };
+        for (uint32_t i = 0; i < locked && rc == DODRT_OK && e == cudaSuccess; i++) {
+            dodrt_scene *s = m->scenes[i];
+            if (!primaryDone[i]) continue;
+            DeviceGuard guard(s->device);
+            e = cudaStreamWaitEvent(s->copyStream, primaryDone[i], 0);
+            if (e == cudaSuccess) e = copyBands(s, i, s->stHits, hits, sizeof(dodrt_hit));
+            for (uint32_t l = 0; l < (uint32_t)shadowDone[i].size() && e == cudaSuccess; l++) {
+                e = cudaStreamWaitEvent(s->copyStream, shadowDone[i][l], 0);
+                if (e == cudaSuccess) e = copyBands(s, i, s->stVis + pixels * l, visible + pixels * l, 1);
+            }
+        }
+        for (uint32_t i = 0; i < locked; i++) { // the staging buffers are re-used by the next call: both streams must have drained
+            dodrt_scene *s = m->scenes[i];
+            DeviceGuard guard(s->device);
+            cudaError_t ec = cudaStreamSynchronize(s->copyStream);
+            cudaError_t es = cudaStreamSynchronize(s->stream);
+            if (e == cudaSuccess) e = ec;
+            if (e == cudaSuccess) e = es;
+        }
+        if (rc != DODRT_OK) return rc;
+        if (e != cudaSuccess) return fail(DODRT_E_CUDA, "dodrt_multi_trace_frame: %s", cudaGetErrorString(e));
+        return DODRT_OK;
+    }
     if (!direct) {
         dodrt_frame_buffer *fb = m->frameBuffer;
         if (!fb || fb->width != frame->width || fb->height != frame->height || fb->numLights < num_lights) {

@@ -256,10 +256,13 @@ DODRT_API int dodrt_frame_buffer_destroy(dodrt_frame_buffer *fb);
  * dodrt_multi renders one frame with all the GPUs of the process: scene replicated (one populated dodrt_scene per GPU,
  * created and filled by the caller with the same arrays), image tiles dealt round-robin over the GPUs, and ONE frame
  * buffer in host memory that every GPU fills in place.  frame describes the whole frame (first_tile / tile_stride /
- * compact are ignored); hits is [height*width], visible [num_lights][height*width], both row-major.  With pinned
- * host buffers (cudaHostAlloc / cudaHostRegister) every GPU's kernel stores its tiles straight into them over its own
- * PCIe link while it traces; with pageable buffers the GPUs assemble the frame in scenes[0]'s HBM over NVLink first and
- * one copy brings it to the host.  Calls on one dodrt_multi are serialised. */
+ * compact, and for dodrt_multi_trace_frame the tile size, are ignored); hits is [height*width], visible
+ * [num_lights][height*width], both row-major.  With pinned host buffers (cudaHostAlloc / cudaHostRegister) the frame is
+ * dealt out in bands of whole pixel rows and every GPU copies its finished bands straight to their place in the
+ * caller's frame over its own PCIe link, the hit records while its shadow pass still runs (DODRT_ZEROCOPY=1: the
+ * kernels store into the mapped host frame themselves instead -- measured slower); with pageable buffers the GPUs
+ * assemble the frame in scenes[0]'s HBM over NVLink first and one copy brings it to the host.  Calls on one dodrt_multi
+ * are serialised. */
 typedef struct dodrt_multi dodrt_multi; /* opaque */
 DODRT_API int dodrt_multi_create(dodrt_scene *const *scenes, uint32_t num_scenes, dodrt_multi **multi);
 DODRT_API int dodrt_multi_trace_frame(dodrt_multi *multi, const dodrt_frame *frame, const float *xs, const float *ys,

@@ -231,6 +231,31 @@ def test_multi_with_one_gpu_and_with_all_gpus():
                 s.close()
 
 
+@pytest.mark.parametrize("w,h", [(1003, 77), (4104, 40), (16, 3)])
+def test_multi_pinned_bands_ragged_and_wide_frames(w, h, monkeypatch):
+    """The staged-band form of dodrt_multi_trace_frame (pinned host frame): widths that are no multiple of 8, frames
+    wider than the tile limit (two bands per row, 2-D copies), fewer bands than GPUs; and the zero-copy form (opt-in)."""
+    import torch
+    scene = teapot_scene(full=True)
+    xs, ys = host.ray_tables(w, h)
+    frame = capi.Frame.make(w, h, classes=ALL)
+    with upload(scene) as g:
+        want_h, want_v = _device_frame(g, frame, xs, ys, LIGHTS2, fused=False)
+    scenes = [upload(scene, d) for d in range(capi.device_count())]
+    try:
+        with capi.Multi(scenes) as m:
+            for zero_copy in ("0", "1"):
+                monkeypatch.setenv("DODRT_ZEROCOPY", zero_copy)
+                ph = torch.zeros((w * h, 16), dtype=torch.uint8).pin_memory().numpy().reshape(-1).view(capi.HIT_DT)
+                pv = torch.zeros((2, w * h), dtype=torch.uint8).pin_memory().numpy()
+                for _ in range(2):
+                    m.trace_frame(frame, xs, ys, LIGHTS2, ph, pv)
+                assert ph.tobytes() == want_h.tobytes() and pv.tobytes() == want_v.tobytes(), f"zero-copy {zero_copy}"
+    finally:
+        for s in scenes:
+            s.close()
+
+
 def test_scene_on_another_device_than_the_current_one():
     """streams / pools must be created on the scene's device, not on the caller's current one."""
     import torch
