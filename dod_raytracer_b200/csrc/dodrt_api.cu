@@ -1711,6 +1711,8 @@ try {
     }
     cudaError_t e = cudaSuccess;
     uint32_t launched = 0;
+    std::vector<std::unique_lock<std::mutex>> hostLocks; // released when the call leaves, whichever way
+    hostLocks.reserve(n);
     for (uint32_t i = 0; i < n && rc == DODRT_OK && e == cudaSuccess; i++) { // asynchronous: all GPUs trace at the same time
         dodrt_scene *s = m->scenes[i];
         DeviceGuard guard(s->device);
@@ -1718,7 +1720,7 @@ try {
             rc = fail(DODRT_E_CUDA, "cannot select device %d", s->device);
             break;
         }
-        s->hostMutex.lock();
+        hostLocks.emplace_back(s->hostMutex);
         launched = i + 1;
         dodrt_frame f = *frame;
         f.first_tile = i;
@@ -1753,7 +1755,6 @@ try {
         DeviceGuard guard(s->device);
         cudaError_t es = cudaStreamSynchronize(s->stream);
         if (e == cudaSuccess) e = es;
-        s->hostMutex.unlock();
     }
     if (rc != DODRT_OK) return rc;
     if (e == cudaSuccess && !direct) {
@@ -1933,6 +1934,8 @@ try {
     }
     int rc = DODRT_OK;
     uint32_t launched = 0;
+    std::vector<std::unique_lock<std::mutex>> hostLocks; // released when the call leaves, whichever way
+    hostLocks.reserve(n);
     for (uint32_t i = 0; i < n && rc == DODRT_OK; i++) {
         dodrt_scene *s = m->scenes[i];
         DeviceGuard guard(s->device);
@@ -1949,7 +1952,7 @@ try {
                 break;
             }
         }
-        s->hostMutex.lock();
+        hostLocks.emplace_back(s->hostMutex);
         launched = i + 1;
         dodrt_frame f = *frame;
         f.first_tile = i;
@@ -1963,7 +1966,6 @@ try {
         DeviceGuard guard(s->device);
         cudaError_t es = cudaStreamSynchronize(s->stream);
         if (e == cudaSuccess) e = es;
-        s->hostMutex.unlock();
     }
     if (d_frame) {
         DeviceGuard guard(m->scenes[0]->device);
