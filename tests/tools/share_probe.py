@@ -24,12 +24,13 @@ def main():
     lights = np.array(w.lights, np.float32)[: (1 if w.shadow else 0)]
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
     st = torch.cuda.current_stream()
+    tile = tuple(int(x) for x in os.environ.get("SHARE_TILE", "32x32").split("x"))  # tile shape of the split (A/B)
     for n in splits:
-        spr = distributed.slots_per_rank(w.width, w.height, n) if n > 1 else w.pixels
+        spr = distributed.slots_per_rank(w.width, w.height, n, tile=tile) if n > 1 else w.pixels
         d_hits = torch.empty((spr, 16), dtype=torch.uint8, device=dev)
         d_vis = torch.empty((1, spr), dtype=torch.uint8, device=dev)
         for r in range(min(nranks, n)):
-            f = distributed.rank_frame(w.width, w.height, w.classes, r, n)
+            f = distributed.rank_frame(w.width, w.height, w.classes, r, n, tile=tile)
             modes = os.environ.get("SHARE_MODES", "fused,queues,separate").split(",")
             out = {m: (float("nan"), float("nan")) for m in ("fused", "queues", "separate")}
             for mode in modes:
