@@ -9,7 +9,7 @@
 // A warp still traversing polls (one volatile load every DeviceScene::donate_poll voted iterations) whether helpers exist; if
 // they outnumber the queued rays it SUSPENDS its live rays -- ray, running clip, best hit, node / leaf cursor and
 // the short stack -- into the queue and goes on to become a helper itself.  A helper resumes ONE ray with the whole
-// warp: kd node steps are warp-uniform, a leaf is tested 32 triangle slots at a time and reduced with the
+// warp: kd node steps are warp-uniform, a leaf is tested 128 triangle slots at a time (four per lane) and reduced with the
 // lexicographic (t, slot) minimum, which is what the reference's slot-by-slot loop with its strict `<` leaves behind
 // (triangle.cpp:119-139) -- the same reduction as leaf_step_coop, bit-identical to every other variant.
 // A suspended ray resumes exactly where it stopped: no node is visited twice, the order of events per ray is the
