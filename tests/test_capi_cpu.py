@@ -90,3 +90,22 @@ def test_host_library_exports_every_declared_symbol():
     lib = host.load()
     for n in names:
         assert getattr(lib, n) is not None, n
+
+
+def test_headers_are_plain_c_and_cxx(tmp_path):
+    """The drop-in boundary is a C ABI: include/dodrt.h and include/dodrt_host.h must compile as C99 on their own
+    (plain pointers and sizes, no C++ or CUDA types), include/dodrt.hpp as C++17 with nothing but the C header."""
+    import shutil
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    if not shutil.which("gcc") or not shutil.which("g++"):
+        pytest.skip("no host compiler")
+    for header in ("dodrt.h", "dodrt_host.h"):
+        src = tmp_path / (header + ".c")
+        src.write_text(f'#include "{header}"\nint main(void) {{ return 0; }}\n')
+        subprocess.run(["gcc", "-std=c99", "-Wall", "-Wextra", "-Werror", "-pedantic", "-fsyntax-only", "-I", os.path.join(root, "include"),
+                        str(src)], check=True)
+    src = tmp_path / "hpp.cpp"
+    src.write_text('#include "dodrt.hpp"\nint main() { return 0; }\n')
+    subprocess.run(["g++", "-std=c++17", "-Wall", "-Wextra", "-Werror", "-fsyntax-only", "-I", os.path.join(root, "include"), str(src)],
+                   check=True)
