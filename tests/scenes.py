@@ -191,3 +191,40 @@ def workload_mesh_files_py(w, directory: str):
         write_dodm_py(path, p, idx)
         out.append(path)
     return out
+
+
+def tie_scene_triangles(kind: str, n: int = 6000, seed: int = 5):
+    """Triangles for the tie-rule tests: vertices on a coarse lattice -- shared edges and vertices,
+    axis-parallel faces -- neighbours in space consecutive in the file; kind "duplicates": every triangle twice, the
+    copies adjacent (same lane), and every 16th once more at the end of the file (another lane, other leaves).
+    Returns (positions [3n, 3] float32, indices [n, 3] uint32)."""
+    rng = np.random.default_rng(seed)
+    c = rng.integers(-4, 5, (n, 1, 3)).astype(np.float64) * 0.5
+    c = c[np.lexsort((c[:, 0, 2], c[:, 0, 1], c[:, 0, 0]))]
+    tri = c + rng.integers(0, 2, (n, 3, 3)) * 0.5
+    if kind == "duplicates":
+        tri = np.repeat(tri[: n // 2], 2, axis=0)
+        tri = np.concatenate([tri, tri[::16]])
+    pos = tri.reshape(-1, 3).astype(np.float32)
+    return pos, np.arange(len(pos), dtype=np.uint32).reshape(-1, 3)
+
+
+def tie_scene_rays(m: int = 40000, seed: int = 6):
+    """Rays along lattice lines, through lattice points (slightly perturbed) and at random; every 4th is any-hit."""
+    rng = np.random.default_rng(seed)
+    o = np.empty((m, 3), np.float32)
+    d = np.empty((m, 3), np.float32)
+    third = m // 3
+    o[:third] = rng.integers(-5, 6, (third, 3)) * 0.5
+    o[:third, 2] = -4.0
+    d[:third] = (0.0, 0.0, 1.0)
+    o[third:2 * third] = rng.integers(-10, 11, (third, 3)) * 0.25
+    tgt = rng.integers(-5, 6, (third, 3)) * 0.5
+    d[third:2 * third] = tgt - o[third:2 * third] + np.float32(1e-3) * rng.standard_normal((third, 3))
+    o[2 * third:] = rng.uniform(-4, 4, (m - 2 * third, 3))
+    d[2 * third:] = rng.standard_normal((m - 2 * third, 3))
+    norm = np.sqrt((d.astype(np.float64) ** 2).sum(axis=1))
+    norm[norm == 0] = 1.0
+    rays = make_rays(o, (d / norm[:, None]).astype(np.float32))
+    rays["flags"][1::4] = 1  # DODRT_RAY_ANY
+    return rays

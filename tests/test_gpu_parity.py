@@ -340,6 +340,30 @@ def test_donated_rays_resume_bit_identically(monkeypatch, oracle):
     assert got.tobytes() == want.tobytes()
 
 
+@pytest.mark.parametrize("kind", ["lattice", "duplicates"])
+def test_tie_rules_on_lattice_and_duplicated_triangles(kind, oracle, monkeypatch):
+    """SURVEY A.5 on the GPU: equal t inside a lane, between the lanes of a leaf and between leaves (lattice triangles
+    with shared edges; every triangle present twice, some three times) -- every variant of this build, and the donating
+    kernel with every ray through the queue, must report the id, t, u, v of the oracle (which tests/test_oracle_vs_ref.py
+    pins against the reference's own code on the same scenes and rays)."""
+    from dod_raytracer_b200 import host
+    from gpu_util import oracle_scene
+    from scenes import tie_scene_rays, tie_scene_triangles
+    pos, idx = tie_scene_triangles(kind)
+    hs = host.HostScene()
+    hs.add_mesh(pos, idx)
+    hs.build_tree()
+    scene = oracle_scene(hs)
+    rays = tie_scene_rays()
+    want = oracle.intersect(scene, rays, CLS_TREE, nthreads=8)
+    assert ((want["prim"] != MISS) & ((rays["flags"] & RAY_ANY) == 0)).sum() > 3000
+    for variant, always in [(v, "0") for v in VARIANTS] + [(7, "1")]:
+        monkeypatch.setenv("DODRT_DONATE_ALWAYS", always)
+        with upload(scene) as g:
+            g.set_kernel_variant(variant)
+            assert_hits_equal(g.intersect(rays, CLS_TREE), want, rays, f"{kind}, variant {variant}, donate-always {always}")
+
+
 @pytest.mark.parametrize("nthreads", [4, 8])
 def test_concurrent_donating_launches(oracle, nthreads):
     """Several host threads trace frames with the donating kernel (variant 7) at the same time, each on its own CUDA

@@ -65,6 +65,32 @@ def test_random_rays_all_classes(teapot_ref, oracle):
     assert (want["prim"][closest] != MISS).sum() > 10000
 
 
+@pytest.mark.parametrize("kind", ["lattice", "duplicates"])
+def test_tie_rules_on_lattice_and_duplicated_triangles(kind, oracle, tmp_path):
+    """equal t inside a lane, between lanes of a leaf and between leaves (a triangle referenced by several
+    leaves, or present twice) must resolve to the id the reference's slot-by-slot loop and leaf order leave behind.
+    Triangles on a coarse lattice (shared edges and vertices, axis-parallel faces) or every triangle twice; rays along
+    lattice lines, through lattice points and at random; ids, t, u, v of the restatement against the reference's code."""
+    from dod_raytracer_b200 import host
+    from scenes import tie_scene_rays, tie_scene_triangles
+    pos, idx = tie_scene_triangles(kind)
+    path = str(tmp_path / f"{kind}.dodm")
+    host.write_dodm(path, pos, idx)
+    ref = RefLib()
+    ref.set_config(64, 64)
+    assert ref.add_mesh(path) == len(idx)
+    ref.build_tree()
+    nodes, lanes, prim, bounds = ref.export_tree()
+    scene = Scene(nodes, lanes, bounds)
+    rays = tie_scene_rays()
+    want = ref.intersect(rays, CLS_TREE, 4)
+    got = oracle.intersect(scene, rays, CLS_TREE, nthreads=4)
+    assert (got["prim"] == want["prim"]).all()
+    closest = (rays["flags"] & RAY_ANY) == 0
+    assert got[closest].tobytes() == want[closest].tobytes()
+    assert (want["prim"][closest] != MISS).sum() > 3000
+
+
 def test_reference_hit_record_is_rebuilt_from_prim_u_v(teapot_ref, oracle):
     """The C ABI returns (t, prim, u, v); the reference's HitRecord (hitrecord.h) must follow from it:
     hitPoint = o + d*t and hitNormal = mat3(AN,BN,CN) * (1-(u+v), u, v) (triangle.cpp:170-174)."""
