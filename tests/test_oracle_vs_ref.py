@@ -65,6 +65,41 @@ def test_random_rays_all_classes(teapot_ref, oracle):
     assert (want["prim"][closest] != MISS).sum() > 10000
 
 
+@pytest.mark.parametrize("kind", ["unnormalised", "axis-parallel", "nan-inf-zero"])
+def test_irregular_rays_all_classes(kind, teapot_ref, oracle):
+    """Rays the reference's arithmetic was not written for, but answers deterministically: directions of length 1e-3 ...
+    1e3 (dodrt_ray.d need not be normalised), one or two zero components (infinite slab inverses, 0 * inf = NaN in
+    box.cpp:38-47), NaN / inf / all-zero directions and NaN origins.  The restatement must follow the reference's
+    compares bit for bit on every class (the GPU path is compared with the restatement on the same kinds of rays in
+    tests/test_gpu_fuzz.py)."""
+    ref, scene = teapot_ref
+    rng = np.random.default_rng(3)
+    n = 30000
+    o = rng.uniform(-4.5, 4.5, (n, 3)).astype(np.float32)
+    d = rng.standard_normal((n, 3)).astype(np.float32)
+    d /= np.linalg.norm(d, axis=1, keepdims=True).astype(np.float32)
+    if kind == "unnormalised":
+        d = (d * np.float32(10.0) ** rng.uniform(-3, 3, (n, 1)).astype(np.float32)).astype(np.float32)
+    elif kind == "axis-parallel":
+        d[np.arange(n), rng.integers(0, 3, n)] = 0.0
+        d[::2, 1] = 0.0
+    else:
+        d[::5, 0] = np.nan
+        d[1::5, 1] = np.inf
+        d[2::5] = 0.0
+        o[3::5, 2] = np.nan
+    rays = make_rays(o, d)
+    rays["flags"][1::4] = RAY_ANY
+    rays["clip"][::3] = rng.uniform(0, 8, len(rays["clip"][::3])).astype(np.float32)
+    closest = (rays["flags"] & RAY_ANY) == 0
+    for cls in (CLS_TREE, CLS_SPHERE, CLS_PLANE, CLS_CYLINDER, ALL):
+        want = ref.intersect(rays, cls, 4)
+        got = oracle.intersect(scene, rays, cls, nthreads=4)
+        assert (got["prim"] == want["prim"]).all(), f"{kind}, classes={cls}"
+        assert got[closest].tobytes() == want[closest].tobytes(), f"{kind}, classes={cls}"
+        assert (want["prim"] != MISS).sum() > 400
+
+
 @pytest.mark.parametrize("kind", ["lattice", "duplicates"])
 def test_tie_rules_on_lattice_and_duplicated_triangles(kind, oracle, tmp_path):
     """equal t inside a lane, between lanes of a leaf and between leaves (a triangle referenced by several
