@@ -228,3 +228,28 @@ def tie_scene_rays(m: int = 40000, seed: int = 6):
     rays = make_rays(o, (d / norm[:, None]).astype(np.float32))
     rays["flags"][1::4] = 1  # DODRT_RAY_ANY
     return rays
+
+
+def irregular_rays(kind: str, n: int = 30000, seed: int = 3):
+    """Rays the reference's arithmetic was not written for but answers deterministically: "unnormalised" = directions
+    of length 1e-3 ... 1e3; "axis-parallel" = one or two zero components (infinite slab inverses, 0 * inf = NaN in
+    box.cpp:38-47); "nan-inf-zero" = NaN / inf / all-zero directions and NaN origins.  A third carry a finite clip,
+    every 4th is any-hit."""
+    rng = np.random.default_rng(seed)
+    o = rng.uniform(-4.5, 4.5, (n, 3)).astype(np.float32)
+    d = rng.standard_normal((n, 3)).astype(np.float32)
+    d /= np.linalg.norm(d, axis=1, keepdims=True).astype(np.float32)
+    if kind == "unnormalised":
+        d = (d * np.float32(10.0) ** rng.uniform(-3, 3, (n, 1)).astype(np.float32)).astype(np.float32)
+    elif kind == "axis-parallel":
+        d[np.arange(n), rng.integers(0, 3, n)] = 0.0
+        d[::2, 1] = 0.0
+    else:
+        d[::5, 0] = np.nan
+        d[1::5, 1] = np.inf
+        d[2::5] = 0.0
+        o[3::5, 2] = np.nan
+    rays = make_rays(o, d)
+    rays["flags"][1::4] = 1  # DODRT_RAY_ANY
+    rays["clip"][::3] = rng.uniform(0, 8, len(rays["clip"][::3])).astype(np.float32)
+    return rays

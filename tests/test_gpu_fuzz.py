@@ -126,3 +126,22 @@ def test_sphere_box_culling_bvh_is_exact(oracle, seed, count, scale):
         g.set_spheres(bscene.sphere_lanes, count)
         want = oracle.intersect(bscene, rays[:20000], CLS_SPHERE, nthreads=8)
         assert_hits_equal(g.intersect(rays[:20000], CLS_SPHERE), want, rays=rays[:20000], what=f"seed {seed} NaN sphere")
+
+
+@pytest.mark.parametrize("kind", ["unnormalised", "axis-parallel", "nan-inf-zero"])
+def test_irregular_rays_all_classes(kind, oracle):
+    """Un-normalised directions against the kd-tree and every analytic class, axis-parallel rays, NaN / inf / zero
+    directions and NaN origins (tests/scenes.py::irregular_rays; the oracle is pinned against the reference's own code
+    on exactly these rays in tests/test_oracle_vs_ref.py): every variant of this build, ids and t, u, v bit-exact --
+    NaN results included."""
+    from gpu_util import upload
+    from scenes import irregular_rays, teapot_scene
+    scene = teapot_scene(full=True)
+    rays = irregular_rays(kind)
+    everything = CLS_SPHERE | CLS_PLANE | CLS_CYLINDER | CLS_TREE
+    with upload(scene) as g:
+        for cls in (CLS_TREE, CLS_SPHERE, CLS_PLANE, CLS_CYLINDER, everything):
+            want = oracle.intersect(scene, rays, cls, nthreads=8)
+            for variant in [v for v in (3, 0, 4, 5, 6, 7, 8) if capi.variant_available(v)]:
+                g.set_kernel_variant(variant)
+                assert_hits_equal(g.intersect(rays, cls), want, rays=rays, what=f"{kind} variant {variant} classes {cls}")

@@ -72,25 +72,9 @@ def test_irregular_rays_all_classes(kind, teapot_ref, oracle):
     box.cpp:38-47), NaN / inf / all-zero directions and NaN origins.  The restatement must follow the reference's
     compares bit for bit on every class (the GPU path is compared with the restatement on the same kinds of rays in
     tests/test_gpu_fuzz.py)."""
+    from scenes import irregular_rays
     ref, scene = teapot_ref
-    rng = np.random.default_rng(3)
-    n = 30000
-    o = rng.uniform(-4.5, 4.5, (n, 3)).astype(np.float32)
-    d = rng.standard_normal((n, 3)).astype(np.float32)
-    d /= np.linalg.norm(d, axis=1, keepdims=True).astype(np.float32)
-    if kind == "unnormalised":
-        d = (d * np.float32(10.0) ** rng.uniform(-3, 3, (n, 1)).astype(np.float32)).astype(np.float32)
-    elif kind == "axis-parallel":
-        d[np.arange(n), rng.integers(0, 3, n)] = 0.0
-        d[::2, 1] = 0.0
-    else:
-        d[::5, 0] = np.nan
-        d[1::5, 1] = np.inf
-        d[2::5] = 0.0
-        o[3::5, 2] = np.nan
-    rays = make_rays(o, d)
-    rays["flags"][1::4] = RAY_ANY
-    rays["clip"][::3] = rng.uniform(0, 8, len(rays["clip"][::3])).astype(np.float32)
+    rays = irregular_rays(kind)
     closest = (rays["flags"] & RAY_ANY) == 0
     for cls in (CLS_TREE, CLS_SPHERE, CLS_PLANE, CLS_CYLINDER, ALL):
         want = ref.intersect(rays, cls, 4)
