@@ -28,3 +28,16 @@ def test_reference_arm_prints_the_contract_line_without_the_product_libraries(tm
     assert cb["kind"] == "reference" and cb["cores"] >= 1 and cb["value"] == line["value"] and cb["sample"]
     assert line["e2e"] == {"value": line["value"], "unit": "Mrays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
     assert line["value"] > 0 and abs(line["ms_per_step"] * 1e-3 * line["value"] * 1e6 - 2 * 1920 * 1080) < 1e-3 * 2 * 1920 * 1080
+
+
+def test_gpu_arm_fails_loudly_without_a_gpu():
+    """No CPU fallback: on a box without a CUDA device the product arm of the bench stops with a message and prints no
+    metric line."""
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--steps", "1", "--workload", "teapot1080"],
+                       capture_output=True, text=True, cwd=ROOT, timeout=600)
+    assert r.returncode != 0
+    assert "no CUDA device" in r.stderr and "no CPU fallback" in r.stderr
+    assert '"metric"' not in r.stdout
